@@ -1,0 +1,148 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE'S OWN SOURCE (read-only at /root/reference) in this container.
+
+GPyTorch is not installable here, so `gpytorch` is replaced by tests/golden/_gpytorch_stub.py (a ~100-line restatement of
+the few upstream classes the reference's kernel modules touch).  The arithmetic of the hot path -- the lines cited in
+each case below -- is the reference's, run verbatim through its classes' `forward` / `conditional_sample` / `log_prob`.
+
+Run:  python tests/golden/make_golden.py      (only in the build container; the GPU box has no /root/reference)
+The resulting fixtures are committed; tests never need /root/reference.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+sys.path.insert(0, HERE)
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+import _gpytorch_stub  # noqa: E402
+
+_gpytorch_stub.install()
+
+import importlib  # noqa: E402
+
+gk = importlib.import_module("models.gibbs_kernels")
+lp = importlib.import_module("models.latent_priors")
+sys.modules["kernels"] = sys.modules["models"]  # sparse_multivariate_gibbs_kernel.py:11 imports a non-existent package
+sys.modules["kernels.latent_priors"] = lp
+mgk = importlib.import_module("models.multivariate_gibbs_kernel")
+smgk = importlib.import_module("models.sparse_multivariate_gibbs_kernel")
+
+
+def npz(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+def gibbs_diag_cases():
+    """GibbsKernel.forward, models/gibbs_kernels.py:135-162 (explicit ell1, ell2; x1 != x2 and x1 == x2 branches)."""
+    torch.set_default_dtype(torch.float64)
+    g = torch.Generator().manual_seed(173)
+    for tag, (n1, n2, D) in {"d1": (17, 9, 1), "d2": (37, 23, 2), "d3": (64, 50, 3), "d5": (12, 20, 5)}.items():
+        x1 = torch.rand(n1, D, generator=g) * 2 - 1
+        x2 = torch.rand(n2, D, generator=g) * 2 - 1
+        ell1 = torch.exp(0.5 * torch.randn(D, n1, generator=g) - 1.0)
+        ell2 = torch.exp(0.5 * torch.randn(D, n2, generator=g) - 1.0)
+        kern = gk.GibbsKernel(lengthscale_prior=None)
+        K12 = kern.forward(x1, x2, ell1=ell1, ell2=ell2)
+        K11 = kern.forward(x1, x1, ell1=ell1)  # torch.equal branch: ell2 = ell1
+        npz("gibbs_diag_" + tag, x1=x1, x2=x2, ell1=ell1, ell2=ell2, K12=K12, K11=K11)
+
+
+def lognormal_field_cases():
+    """LogNormalPriorProcess.conditional_sample / log_prob, models/gibbs_kernels.py:80-109, and GibbsKernel.forward with
+    ell2=None (conditional branch :151-153)."""
+    torch.set_default_dtype(torch.float64)
+    g = torch.Generator().manual_seed(174)
+    for tag, (n, m, D) in {"d2": (40, 15, 2), "d3": (33, 20, 3)}.items():
+        prior = gk.LogNormalPriorProcess(input_dim=D)
+        os_ = 0.5 + torch.rand(D, generator=g)
+        lam = 0.8 + torch.rand(D, 1, D, generator=g)
+        c = torch.log(torch.tensor(0.3)) + 0.1 * torch.randn(D, 1, generator=g)
+        prior.covar_module.outputscale = os_
+        prior.covar_module.base_kernel.lengthscale = lam
+        prior.mean_module.constant.data = c
+        xg = torch.rand(m, D, generator=g) * 2 - 1
+        x = torch.rand(n, D, generator=g) * 2 - 1
+        ell_g = torch.exp(torch.log(torch.tensor(0.3)) + 0.3 * torch.randn(D, m, generator=g))
+        with torch.no_grad():
+            ell_x = prior.conditional_sample(x, given=(xg, ell_g))
+            logp = prior.log_prob((xg, torch.log(ell_g)))
+            kern = gk.GibbsKernel(lengthscale_prior=prior)
+            K = kern.forward(xg, x, ell1=ell_g)  # ell2 sampled conditionally at x given (xg, ell_g)
+        npz("lognormal_field_" + tag, x=x, xg=xg, ell_g=ell_g, c=c.squeeze(-1), os=os_, lam=lam.squeeze(1), ell_x=ell_x,
+            log_prob=logp, K_cond=K)
+
+
+def _bare(cls, H, D, d):
+    k = cls.__new__(cls)
+    torch.nn.Module.__init__(k)
+    k.d = d
+    k.H = torch.nn.Parameter(H.clone())
+    k.D = torch.nn.Parameter(D.clone())
+    return k
+
+
+def multivariate_cases():
+    """MultivariateGibbsKernel.forward, models/multivariate_gibbs_kernel.py:77-150 (same-input branch :79-106 and cross
+    branch :108-143), once with default dtype float64 (all-fp64 through the reference's own lines) and once with the
+    default float32 as shipped (Sigma silently float32)."""
+    for dtname, dt in (("f64", torch.float64), ("f32sigma", torch.float32)):
+        torch.set_default_dtype(dt)
+        g = torch.Generator().manual_seed(175)
+        n1, n2, d = 30, 19, 2
+        x1 = (torch.rand(n1, d, generator=g, dtype=torch.float64) * 2 - 1)
+        x2 = (torch.rand(n2, d, generator=g, dtype=torch.float64) * 2 - 1)
+        H1 = torch.randn(n1, d, generator=g, dtype=torch.float64)
+        H2 = torch.randn(n2, d, generator=g, dtype=torch.float64)
+        Dm = torch.diag(torch.tensor([0.6, -0.9], dtype=torch.float64))
+        k = _bare(mgk.MultivariateGibbsKernel, H1.to(dt), Dm, d)
+        k.expectation_conditional_matrix_variate_dist = lambda xs: H2.to(dt)  # conditional mean supplied directly
+        import contextlib
+        import io
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            K11 = k.forward(x1, x1)
+            K12 = k.forward(x1, x2)
+        npz("gibbs_full_d2_" + dtname, x1=x1, x2=x2, H1=H1, H2=H2, Dm=Dm, K11=K11, K12=K12)
+    torch.set_default_dtype(torch.float64)
+
+
+def sparse_multivariate_cases():
+    """SparseMultivariateGibbsKernel: full constructor (:29-65), conditional mean of H (:67-80) and forward on inputs
+    whose row count differs from M (:92-100, :113-123); default dtype float64."""
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(176)
+    g = torch.Generator().manual_seed(176)
+    M, n, d = 12, 25, 2
+    Z = torch.rand(M, d, generator=g) * 2 - 1
+    x = torch.rand(n, d, generator=g) * 2 - 1
+    import contextlib
+    import io
+    k = smgk.SparseMultivariateGibbsKernel(Z, d, Z.clone())
+    k.H.data = k.H.data.double()
+    k.D.data = torch.diag(torch.tensor([0.7, 0.5]))
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        Hx = k.expectation_conditional_matrix_variate_dist(x)
+        Kxz = k.forward(x, Z)
+        Kzz = k.forward(Z, Z)
+        Kxx = k.forward(x, x)
+        logp = k.H_matrix_prior.log_prob(k.H.data)
+    npz("sparse_multivariate_d2", Z=Z, x=x, H=k.H.data, Dm=k.D.data, row_os=k.row_covar_kernel.outputscale,
+        row_lam=k.row_covar_kernel.base_kernel.lengthscale.reshape(-1), Hx=Hx, Kxz=Kxz, Kzz=Kzz, Kxx=Kxx,
+        prior_H_log_prob=logp)
+
+
+if __name__ == "__main__":
+    gibbs_diag_cases()
+    lognormal_field_cases()
+    multivariate_cases()
+    sparse_multivariate_cases()
