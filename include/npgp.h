@@ -1,0 +1,105 @@
+/* npgp -- C ABI of the B200-native non-stationary (Gibbs) GP hot path.
+ *
+ * Every entry point takes raw DEVICE pointers (fp64, row-major), explicit sizes / leading dimensions and the CUDA
+ * stream to run on; nothing allocates, nothing synchronises, nothing keeps global mutable state.  Return value:
+ * 0 = ok, < 0 = argument error (NPGP_E*), > 0 = a cudaError_t from the launch.  All calls are asynchronous.
+ * Outputs documented as "accumulated" are added to with atomics and must be zeroed by the caller.
+ *
+ * The reference (Stansfash/nonstationary-precip) has no native code and no FFI: the interfaces replaced here are the
+ * Python methods cited per function (file:line into the reference), which the host-side mirror in
+ * nonstationary_precip_b200/ re-implements on top of this library.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef NPGP_H_
+#define NPGP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* npgp_stream_t; /* == cudaStream_t */
+
+#define NPGP_OK 0
+#define NPGP_EINVAL (-1)
+#define NPGP_EUNSUPPORTED (-2)
+#define NPGP_EWORKSPACE (-3)
+
+int npgp_version(void);
+
+/* ---- (a) fused Gibbs cross-covariance tiles ------------------------------------------------------------------------
+ * Diagonal Gibbs kernel, replaces GibbsKernel.forward (models/gibbs_kernels.py:135-162).
+ *   x1 (n1,D), x2 (n2,D) row-major; ell1 (D,n1), ell2 (D,n2) dim-major (layout of nonstationary_models.py:31-34);
+ *   scale: optional device scalar (outputscale, GibbsSafeScaleKernel gibbs_kernels.py:164-168); K (n1,n2), ld = ldk.
+ *   Optional fused mat-vec: Ku[i] += sum_j K_ij u_j (accumulated).  D = 1..6. */
+int npgp_gibbs_diag_fwd(int D, int n1, int n2, const double* x1, const double* ell1, const double* x2,
+                        const double* ell2, const double* scale, double* K, long ldk, const double* u, double* Ku,
+                        npgp_stream_t stream);
+/* Analytic backward (replaces the autograd graph of the same lines).  Upstream gradient
+ *   G_ij = rowscale_i * G[i,j] + rowvec_i * colvec_j   (G or the rank-1 part may be NULL; rowscale NULL = 1).
+ * Accumulated outputs: d_ell1 (D,n1), d_ell2 (D,n2), optional d_x1 (n1,D), d_x2 (n2,D), d_scale (scalar). */
+int npgp_gibbs_diag_bwd(int D, int n1, int n2, const double* x1, const double* ell1, const double* x2,
+                        const double* ell2, const double* scale, const double* G, long ldg, const double* rowscale,
+                        const double* rowvec, const double* colvec, double* d_ell1, double* d_x1, double* d_ell2,
+                        double* d_x2, double* d_scale, npgp_stream_t stream);
+
+/* Full-matrix (Paciorek-Schervish) Gibbs kernel, d = 2 or 3; replaces MultivariateGibbsKernel.forward
+ * (models/multivariate_gibbs_kernel.py:101-150) and SparseMultivariateGibbsKernel.forward
+ * (models/sparse_multivariate_gibbs_kernel.py:105-154).  S1 (n1,P), S2 (n2,P): packed symmetric per-point matrices,
+ * P = d(d+1)/2, d=2 [00,01,11], d=3 [00,01,02,11,12,22].  jitter: the reference's 1e-5 on the inverse only. */
+int npgp_gibbs_full_fwd(int d, int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
+                        double jitter, const double* scale, double* K, long ldk, const double* u, double* Ku,
+                        npgp_stream_t stream);
+/* d_S1 (n1,P), d_S2 (n2,P) accumulated: entries of the SYMMETRIC matrix dL/dSigma in the same packing. */
+int npgp_gibbs_full_bwd(int d, int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
+                        double jitter, const double* scale, const double* G, long ldg, const double* rowscale,
+                        const double* rowvec, const double* colvec, double* d_S1, double* d_x1, double* d_S2,
+                        double* d_x2, double* d_scale, npgp_stream_t stream);
+
+/* Sigma(h) = softplus((h h^T)o(h h^T)) + DoD (models/multivariate_gibbs_kernel.py:98); H (n,d), Dm (d,d) -> S (n,P).
+ * Backward: dH (n,d) and dDm (d,d) accumulated (dDm may be NULL). */
+int npgp_sigma_from_h_fwd(int d, int n, const double* H, const double* Dm, double* S, npgp_stream_t stream);
+int npgp_sigma_from_h_bwd(int d, int n, const double* H, const double* Dm, const double* dS, double* dH, double* dDm,
+                          npgp_stream_t stream);
+
+/* ---- (b) matrix-free / tensor-core contractions ---------------------------------------------------------------------
+ * Lengthscale-field interpolation, matrix free:
+ *   out[b,i,c] = f( bias_b + sum_j os_b exp(-0.5 |(x_i - z_j)/lam_b|^2) V[b,j,c] ),  f = exp if apply_exp else identity
+ * x (n,d), z (m,d), lam (nb,d), os (nb) or NULL, V (nb,m,nv), bias (nb) or NULL, out (nb,n,nv).
+ * Replaces LogNormalPriorProcess.conditional_sample's K_xg @ alpha (models/gibbs_kernels.py:85-100; nb = D, nv = 1) and
+ * expectation_conditional_matrix_variate_dist (models/sparse_multivariate_gibbs_kernel.py:67-80; nb = 1, nv = d).
+ * Backward (w.r.t. the pre-f value): dV (nb,m,nv) and dz (m,d, may be NULL) accumulated. */
+int npgp_rbf_matvec_fwd(int d, int nb, int nv, int n, int m, const double* x, const double* z, const double* lam,
+                        const double* os, const double* V, const double* bias, int apply_exp, double* out,
+                        npgp_stream_t stream);
+int npgp_rbf_matvec_bwd(int d, int nb, int nv, int n, int m, const double* x, const double* z, const double* lam,
+                        const double* os, const double* V, const double* dOut, double* dV, double* dz,
+                        npgp_stream_t stream);
+
+/* FP64 tensor-core GEMM (DMMA), row-major: C = alpha op(A) op(B) + beta C.  tri_a / tri_b: structure of op(A) (MxK) /
+ * op(B) (KxN): 0 dense, 1 lower, 2 upper (zero blocks are skipped); out_tri: 0 all, 1 lower tiles only, 2 upper only.
+ * lda, ldb must be even and A, B 16-byte aligned. */
+int npgp_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
+               long ldb, double beta, double* C, long ldc, int tri_a, int tri_b, int out_tri, npgp_stream_t stream);
+/* T = K C and q_i = sum_j T_ij K_ij (q accumulated, may be NULL): the A^T (S - I) A term of the whitened predictive
+ * variance (GPyTorch VariationalStrategy.forward as driven by models/dgps.py:25-35) with C = L^-T (S - I) L^-1. */
+int npgp_rowquad(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
+                 npgp_stream_t stream);
+/* Out = alpha K^T diag(w) K (symmetric, overwritten); w NULL = ones.  dL/dC of the SVGP ELBO and the SGPR
+ * Phi = Kzx Kxz (models/gibbs_kernels.py:222-225). */
+int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const double* w, double* Out, long ldo,
+               npgp_stream_t stream);
+int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t stream);
+
+/* ---- (c) blocked Cholesky + inverse factor --------------------------------------------------------------------------
+ * A = L L^T in place (upper zeroed), P = L^-1; *info = 0 or 1-based index of the first non-positive pivot.
+ * Replaces psd_safe_cholesky + triangular_solve(eye, chol) (models/gibbs_kernels.py:197-208). */
+long npgp_potrf_workspace_bytes(int M);
+int npgp_potrf_inv_lower(int M, double* A, long lda, double* P, long ldp, void* work, long work_bytes, int* info,
+                         npgp_stream_t stream);
+
+/* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
+int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPGP_H_ */

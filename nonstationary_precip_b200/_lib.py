@@ -1,0 +1,89 @@
+"""ctypes binding of libnpgp.so (C ABI declared in include/npgp.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  PyTorch is used only to own device
+memory and to name the CUDA stream the kernels are enqueued on."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnpgp.so")
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_long
+_d = C.c_double
+
+_SIGS = {
+    "npgp_version": ([], _i),
+    "npgp_gibbs_diag_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p], _i),
+    "npgp_gibbs_diag_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p], _i),
+    "npgp_gibbs_full_fwd": ([_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _l, _p, _p, _p], _i),
+    "npgp_gibbs_full_bwd": ([_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p], _i),
+    "npgp_sigma_from_h_fwd": ([_i, _i, _p, _p, _p, _p], _i),
+    "npgp_sigma_from_h_bwd": ([_i, _i, _p, _p, _p, _p, _p, _p], _i),
+    "npgp_rbf_matvec_fwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p], _i),
+    "npgp_rbf_matvec_bwd": ([_i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p], _i),
+    "npgp_dgemm": ([_i, _i, _i, _i, _i, _d, _p, _l, _p, _l, _d, _p, _l, _i, _i, _i, _p], _i),
+    "npgp_rowquad": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
+    "npgp_wsyrk": ([_i, _i, _d, _p, _l, _p, _p, _l, _p], _i),
+    "npgp_symmetrize": ([_i, _p, _l, _i, _p], _i),
+    "npgp_potrf_workspace_bytes": ([_i], _l),
+    "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
+    "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
+}
+
+_lib = None
+
+
+class NpgpError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def lib():
+    """Load libnpgp.so (once).  Raises if it has not been built -- there is no CPU or eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NpgpError(
+                "libnpgp.so not found at %s: build it with `python -m nonstationary_precip_b200.build` "
+                "(the CUDA extension is mandatory; there is no fallback path)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    if rc < 0:
+        msg = {-1: "invalid argument", -2: "unsupported configuration", -3: "workspace too small"}.get(rc, "error")
+    else:
+        msg = "CUDA error %d" % rc
+    raise NpgpError("%s failed: %s" % (what, msg))
+
+
+def ptr(t):
+    """Raw device pointer of a CUDA fp64 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NpgpError("npgp kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device.type)
+    if t.dtype not in (torch.float64, torch.int32):
+        raise NpgpError("npgp kernels are fp64 (got %s)" % t.dtype)
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

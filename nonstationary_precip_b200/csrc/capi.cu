@@ -1,0 +1,4 @@
+// Library identity for the C ABI (include/npgp.h).
+#include "common.cuh"
+
+extern "C" int npgp_version(void) { return 100; }  // 0.1.0

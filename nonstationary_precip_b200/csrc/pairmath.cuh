@@ -1,0 +1,196 @@
+// Per-pair arithmetic of the Gibbs kernels, shared by every tile kernel.  __host__ __device__ so that the formulas can
+// also be checked on a CPU (tests/hostcheck) -- the product only ever calls them from CUDA kernels.
+//
+// Diagonal kernel  (reference: models/gibbs_kernels.py:154-162):
+//     K_ij = prod_d sqrt(2 l_id l_jd / s_d) * exp(-sum_d delta_d^2 / s_d),  s_d = l_id^2 + l_jd^2
+//   evaluated in common-denominator form with P = prod_d s_d, r = rsqrt(P):
+//     K_ij = c_i c_j r exp(-r^2 sum_d delta_d^2 prod_{e!=d} s_e),   c_i = sqrt(2^{D/2} prod_d l_id)
+//   -> one rsqrt + one exp per pair, no division.
+// Full-matrix kernel (reference: models/multivariate_gibbs_kernel.py:101-150):
+//     K_ij = det(S_i)^(1/4) det(S_j)^(1/4) det(A)^(-1/2) exp(-delta^T (A + eps I)^-1 delta),  A = (S_i + S_j)/2
+//   with At = S_i + S_j:  det(A) = det(At)/2^d,  (A + eps I)^-1 = 2 (At + 2 eps I)^-1 = 2 adj(Bt)/det(Bt).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define NPGP_HD __host__ __device__ __forceinline__
+#else
+#define NPGP_HD inline
+#endif
+
+namespace npgp {
+
+NPGP_HD double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int sym_size(int d) { return d * (d + 1) / 2; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// diagonal Gibbs
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D>
+struct DiagPair {
+  double k;       // unscaled kernel value
+  double is[D];   // 1 / s_d
+  double dl[D];   // delta_d = x_id - z_jd
+};
+
+// xi, ai = l_i^2, ci as above (row point); zj, bj, cj (column point)
+template <int D>
+NPGP_HD double gibbs_diag_eval(const double* xi, const double* ai, double ci, const double* zj, const double* bj,
+                               double cj, DiagPair<D>* out = nullptr) {
+  double s[D], dl[D], pre[D + 1], suf[D + 1];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    s[d] = ai[d] + bj[d];
+    dl[d] = xi[d] - zj[d];
+  }
+  pre[0] = 1.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) pre[d + 1] = pre[d] * s[d];
+  suf[D] = 1.0;
+#pragma unroll
+  for (int d = D - 1; d >= 0; --d) suf[d] = suf[d + 1] * s[d];
+  const double P = pre[D];
+  double num = 0.0;
+  double pe[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    pe[d] = pre[d] * suf[d + 1];
+    num = fma(dl[d] * dl[d], pe[d], num);
+  }
+  const double r = fast_rsqrt(P);
+  const double r2 = r * r;
+  const double k = (ci * cj) * r * exp(-num * r2);
+  if (out) {
+    out->k = k;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      out->is[d] = pe[d] * r2;
+      out->dl[d] = dl[d];
+    }
+  }
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small symmetric matrices, packed row-wise upper triangle: d=2 [00,01,11]; d=3 [00,01,02,11,12,22]
+// ---------------------------------------------------------------------------------------------------------------------
+template <int d>
+NPGP_HD void sym_adj_det(const double* m, double* adj, double& det);
+
+template <>
+NPGP_HD void sym_adj_det<2>(const double* m, double* adj, double& det) {
+  adj[0] = m[2];
+  adj[1] = -m[1];
+  adj[2] = m[0];
+  det = fma(m[0], m[2], -m[1] * m[1]);
+}
+
+template <>
+NPGP_HD void sym_adj_det<3>(const double* m, double* adj, double& det) {
+  adj[0] = fma(m[3], m[5], -m[4] * m[4]);
+  adj[1] = fma(m[2], m[4], -m[1] * m[5]);
+  adj[2] = fma(m[1], m[4], -m[2] * m[3]);
+  adj[3] = fma(m[0], m[5], -m[2] * m[2]);
+  adj[4] = fma(m[1], m[2], -m[0] * m[4]);
+  adj[5] = fma(m[0], m[3], -m[1] * m[1]);
+  det = fma(m[0], adj[0], fma(m[1], adj[1], m[2] * adj[2]));
+}
+
+template <int d>
+NPGP_HD double sym_det(const double* m) {
+  double adj[sym_size(d)], det;
+  sym_adj_det<d>(m, adj, det);
+  return det;
+}
+
+// y = M v for packed symmetric M
+template <int d>
+NPGP_HD void sym_matvec(const double* m, const double* v, double* y);
+template <>
+NPGP_HD void sym_matvec<2>(const double* m, const double* v, double* y) {
+  y[0] = fma(m[0], v[0], m[1] * v[1]);
+  y[1] = fma(m[1], v[0], m[2] * v[1]);
+}
+template <>
+NPGP_HD void sym_matvec<3>(const double* m, const double* v, double* y) {
+  y[0] = fma(m[0], v[0], fma(m[1], v[1], m[2] * v[2]));
+  y[1] = fma(m[1], v[0], fma(m[3], v[1], m[4] * v[2]));
+  y[2] = fma(m[2], v[0], fma(m[4], v[1], m[5] * v[2]));
+}
+
+// packed index helper (compile-time unrolled loops use it)
+NPGP_HD int sym_idx(int d, int k, int l) {  // k <= l
+  return k * d - (k * (k - 1)) / 2 + (l - k);
+}
+
+template <int d>
+struct FullPair {
+  double k;                  // unscaled kernel value
+  double w[d];               // (A + eps I)^-1 delta
+  double hA[sym_size(d)];    // 0.5 * adj(At)/det(At) = 0.25 * A^-1
+};
+
+// xi, Si (packed), qi = det(Si)^(1/4); likewise column point.  jit2 = 2 * jitter.
+template <int d>
+NPGP_HD double gibbs_full_eval(const double* xi, const double* Si, double qi, const double* zj, const double* Sj,
+                               double qj, double jit2, FullPair<d>* out = nullptr) {
+  constexpr int P = sym_size(d);
+  double At[P], Bt[P], adjA[P], adjB[P], detA, detB, dl[d], v[d];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    At[p] = Si[p] + Sj[p];
+    Bt[p] = At[p];
+  }
+#pragma unroll
+  for (int k = 0; k < d; ++k) {
+    Bt[sym_idx(d, k, k)] += jit2;
+    dl[k] = xi[k] - zj[k];
+  }
+  sym_adj_det<d>(At, adjA, detA);
+  sym_adj_det<d>(Bt, adjB, detB);
+  sym_matvec<d>(adjB, dl, v);
+  double dv = 0.0;
+#pragma unroll
+  for (int k = 0; k < d; ++k) dv = fma(dl[k], v[k], dv);
+  const double idetB2 = 2.0 / detB;
+  const double r = fast_rsqrt(detA);
+  // det(A)^(-1/2) = 2^(d/2) rsqrt(det At)
+  const double pow2 = (d == 2) ? 2.0 : 2.8284271247461900976;
+  const double k = (qi * qj) * (pow2 * r) * exp(-dv * idetB2);
+  if (out) {
+    out->k = k;
+    const double hr2 = 0.5 * r * r;
+#pragma unroll
+    for (int a = 0; a < d; ++a) out->w[a] = v[a] * idetB2;
+#pragma unroll
+    for (int p = 0; p < P; ++p) out->hA[p] = adjA[p] * hr2;
+  }
+  return k;
+}
+
+// softplus with torch's threshold (20): Sigma_kl = softplus(u^2) + D_kl^2, u = h_k h_l
+NPGP_HD double softplus20(double t) { return t > 20.0 ? t : log1p(exp(t)); }
+NPGP_HD double sigmoid20(double t) { return t > 20.0 ? 1.0 : 1.0 / (1.0 + exp(-t)); }
+
+template <int d>
+NPGP_HD void sigma_from_h_row(const double* h, const double* Dm /* d x d row-major */, double* S /* packed */) {
+#pragma unroll
+  for (int k = 0; k < d; ++k)
+#pragma unroll
+    for (int l = k; l < d; ++l) {
+      const double u = h[k] * h[l];
+      S[sym_idx(d, k, l)] = softplus20(u * u) + Dm[k * d + l] * Dm[k * d + l];
+    }
+}
+
+}  // namespace npgp

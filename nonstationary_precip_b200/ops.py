@@ -1,0 +1,299 @@
+"""Torch-facing wrappers of the npgp C ABI: raw launchers (no autograd) and ``torch.autograd.Function``s whose backward
+is the hand-written analytic kernel, not an autograd graph.  Every function enqueues on the current CUDA stream and
+returns without synchronising."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream
+
+
+def _c(t: Optional[torch.Tensor]):
+    return None if t is None else t.contiguous()
+
+
+def sym_pack(S: torch.Tensor) -> torch.Tensor:
+    """(n,d,d) symmetric -> (n, d(d+1)/2) row-wise upper triangle."""
+    d = S.shape[-1]
+    iu = torch.triu_indices(d, d, device=S.device)
+    return S[..., iu[0], iu[1]].contiguous()
+
+
+def sym_unpack(Sp: torch.Tensor, d: int) -> torch.Tensor:
+    iu = torch.triu_indices(d, d, device=Sp.device)
+    S = Sp.new_zeros(*Sp.shape[:-1], d, d)
+    S[..., iu[0], iu[1]] = Sp
+    S[..., iu[1], iu[0]] = Sp
+    return S
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# raw launchers
+# ----------------------------------------------------------------------------------------------------------------------
+def gibbs_diag_fwd(x1, ell1, x2, ell2, scale=None, u=None, out=None):
+    """K = scale * GibbsKernel(x1, x2; ell1, ell2).  x (n,D), ell (D,n).  Returns K or (K, K@u)."""
+    x1, ell1, x2, ell2, scale, u = map(_c, (x1, ell1, x2, ell2, scale, u))
+    n1, D = x1.shape
+    n2 = x2.shape[0]
+    assert ell1.shape == (D, n1) and ell2.shape == (D, n2), "lengthscales must be (D, n)"
+    K = out if out is not None else torch.empty(n1, n2, dtype=torch.float64, device=x1.device)
+    Ku = torch.zeros(n1, dtype=torch.float64, device=x1.device) if u is not None else None
+    check(lib().npgp_gibbs_diag_fwd(D, n1, n2, ptr(x1), ptr(ell1), ptr(x2), ptr(ell2), ptr(scale), ptr(K), K.stride(0),
+                                    ptr(u), ptr(Ku), stream()), "npgp_gibbs_diag_fwd")
+    return K if u is None else (K, Ku)
+
+
+def gibbs_diag_bwd(x1, ell1, x2, ell2, scale=None, G=None, rowscale=None, rowvec=None, colvec=None, need_dx1=False,
+                   need_dx2=False, need_dscale=False):
+    x1, ell1, x2, ell2, scale, G, rowscale, rowvec, colvec = map(
+        _c, (x1, ell1, x2, ell2, scale, G, rowscale, rowvec, colvec))
+    n1, D = x1.shape
+    n2 = x2.shape[0]
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=x1.device)
+    d_ell1, d_ell2 = z(D, n1), z(D, n2)
+    d_x1 = z(n1, D) if need_dx1 else None
+    d_x2 = z(n2, D) if need_dx2 else None
+    d_scale = z(()) if need_dscale else None
+    check(lib().npgp_gibbs_diag_bwd(D, n1, n2, ptr(x1), ptr(ell1), ptr(x2), ptr(ell2), ptr(scale), ptr(G),
+                                    G.stride(0) if G is not None else 0, ptr(rowscale), ptr(rowvec), ptr(colvec),
+                                    ptr(d_ell1), ptr(d_x1), ptr(d_ell2), ptr(d_x2), ptr(d_scale), stream()),
+          "npgp_gibbs_diag_bwd")
+    return dict(d_ell1=d_ell1, d_ell2=d_ell2, d_x1=d_x1, d_x2=d_x2, d_scale=d_scale)
+
+
+def gibbs_full_fwd(x1, S1p, x2, S2p, jitter=1e-5, scale=None, u=None, out=None):
+    """K = scale * full-matrix Gibbs kernel; S?p packed symmetric (n, d(d+1)/2)."""
+    x1, S1p, x2, S2p, scale, u = map(_c, (x1, S1p, x2, S2p, scale, u))
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    P = d * (d + 1) // 2
+    assert S1p.shape == (n1, P) and S2p.shape == (n2, P)
+    K = out if out is not None else torch.empty(n1, n2, dtype=torch.float64, device=x1.device)
+    Ku = torch.zeros(n1, dtype=torch.float64, device=x1.device) if u is not None else None
+    check(lib().npgp_gibbs_full_fwd(d, n1, n2, ptr(x1), ptr(S1p), ptr(x2), ptr(S2p), float(jitter), ptr(scale), ptr(K),
+                                    K.stride(0), ptr(u), ptr(Ku), stream()), "npgp_gibbs_full_fwd")
+    return K if u is None else (K, Ku)
+
+
+def gibbs_full_bwd(x1, S1p, x2, S2p, jitter=1e-5, scale=None, G=None, rowscale=None, rowvec=None, colvec=None,
+                   need_dx1=False, need_dx2=False, need_dscale=False):
+    x1, S1p, x2, S2p, scale, G, rowscale, rowvec, colvec = map(
+        _c, (x1, S1p, x2, S2p, scale, G, rowscale, rowvec, colvec))
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    P = d * (d + 1) // 2
+    z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=x1.device)
+    d_S1, d_S2 = z(n1, P), z(n2, P)
+    d_x1 = z(n1, d) if need_dx1 else None
+    d_x2 = z(n2, d) if need_dx2 else None
+    d_scale = z(()) if need_dscale else None
+    check(lib().npgp_gibbs_full_bwd(d, n1, n2, ptr(x1), ptr(S1p), ptr(x2), ptr(S2p), float(jitter), ptr(scale), ptr(G),
+                                    G.stride(0) if G is not None else 0, ptr(rowscale), ptr(rowvec), ptr(colvec),
+                                    ptr(d_S1), ptr(d_x1), ptr(d_S2), ptr(d_x2), ptr(d_scale), stream()),
+          "npgp_gibbs_full_bwd")
+    return dict(d_S1=d_S1, d_S2=d_S2, d_x1=d_x1, d_x2=d_x2, d_scale=d_scale)
+
+
+def sigma_from_h_fwd(H, Dm):
+    H, Dm = _c(H), _c(Dm)
+    n, d = H.shape
+    S = torch.empty(n, d * (d + 1) // 2, dtype=torch.float64, device=H.device)
+    check(lib().npgp_sigma_from_h_fwd(d, n, ptr(H), ptr(Dm), ptr(S), stream()), "npgp_sigma_from_h_fwd")
+    return S
+
+
+def sigma_from_h_bwd(H, Dm, dS, need_dD=True):
+    H, Dm, dS = _c(H), _c(Dm), _c(dS)
+    n, d = H.shape
+    dH = torch.zeros_like(H)
+    dD = torch.zeros_like(Dm) if need_dD else None
+    check(lib().npgp_sigma_from_h_bwd(d, n, ptr(H), ptr(Dm), ptr(dS), ptr(dH), ptr(dD), stream()),
+          "npgp_sigma_from_h_bwd")
+    return dH, dD
+
+
+def rbf_matvec_fwd(x, z, lam, os, V, bias=None, apply_exp=False):
+    """out[b,i,c] = f(bias_b + sum_j os_b exp(-0.5|(x_i-z_j)/lam_b|^2) V[b,j,c]);  lam (nb,d), V (nb,m,nv)."""
+    x, z, lam, os, V, bias = map(_c, (x, z, lam, os, V, bias))
+    n, d = x.shape
+    nb, m, nv = V.shape
+    assert lam.shape == (nb, d)
+    out = torch.empty(nb, n, nv, dtype=torch.float64, device=x.device)
+    check(lib().npgp_rbf_matvec_fwd(d, nb, nv, n, m, ptr(x), ptr(z), ptr(lam), ptr(os), ptr(V), ptr(bias),
+                                    int(apply_exp), ptr(out), stream()), "npgp_rbf_matvec_fwd")
+    return out
+
+
+def rbf_matvec_bwd(x, z, lam, os, V, dOut, need_dz=True):
+    x, z, lam, os, V, dOut = map(_c, (x, z, lam, os, V, dOut))
+    n, d = x.shape
+    nb, m, nv = V.shape
+    dV = torch.zeros_like(V)
+    dz = torch.zeros_like(z) if need_dz else None
+    check(lib().npgp_rbf_matvec_bwd(d, nb, nv, n, m, ptr(x), ptr(z), ptr(lam), ptr(os), ptr(V), ptr(dOut), ptr(dV),
+                                    ptr(dz), stream()), "npgp_rbf_matvec_bwd")
+    return dV, dz
+
+
+def dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None, tri_a=0, tri_b=0, out_tri=0):
+    """C = alpha op(A) op(B) + beta C on the FP64 tensor pipe.  A, B may be views with unit inner stride."""
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
+    M = A.shape[1] if transA else A.shape[0]
+    Kd = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == Kd
+    if C is None:
+        C = torch.empty(M, N, dtype=torch.float64, device=A.device)
+        assert beta == 0.0
+    check(lib().npgp_dgemm(int(transA), int(transB), M, N, Kd, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0),
+                           float(beta), ptr(C), C.stride(0), tri_a, tri_b, out_tri, stream()), "npgp_dgemm")
+    return C
+
+
+def rowquad(K, Cm, need_q=True, T=None):
+    """T = K @ Cm, q_i = sum_j T_ij K_ij."""
+    n, M = K.shape
+    if T is None:
+        T = torch.empty(n, M, dtype=torch.float64, device=K.device)
+    q = torch.zeros(n, dtype=torch.float64, device=K.device) if need_q else None
+    check(lib().npgp_rowquad(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q), stream()),
+          "npgp_rowquad")
+    return T, q
+
+
+def wsyrk(K, w=None, alpha=1.0, out=None):
+    """alpha * K^T diag(w) K (symmetric M x M)."""
+    n, M = K.shape
+    if out is None:
+        out = torch.empty(M, M, dtype=torch.float64, device=K.device)
+    check(lib().npgp_wsyrk(n, M, float(alpha), ptr(K), K.stride(0), ptr(_c(w)), ptr(out), out.stride(0), stream()),
+          "npgp_wsyrk")
+    return out
+
+
+def potrf_inv(A, overwrite=False):
+    """Lower Cholesky factor L of A and P = L^-1.  Returns (L, P, info) with info a device int32 scalar
+    (0 = ok, else 1-based index of the first non-positive pivot)."""
+    M = A.shape[0]
+    L = A if overwrite else A.clone()
+    assert L.is_contiguous()
+    P = torch.empty_like(L)
+    nbytes = lib().npgp_potrf_workspace_bytes(M)
+    work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=A.device)
+    info = torch.zeros((), dtype=torch.int32, device=A.device)
+    check(lib().npgp_potrf_inv_lower(M, ptr(L), L.stride(0), ptr(P), P.stride(0), ptr(work), nbytes, ptr(info),
+                                     stream()), "npgp_potrf_inv_lower")
+    return L, P, info
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# autograd Functions (analytic backward kernels)
+# ----------------------------------------------------------------------------------------------------------------------
+class GibbsDiagFn(torch.autograd.Function):
+    """K = scale * GibbsKernel(x1,x2;ell1,ell2) with gradients to x1, ell1, x2, ell2, scale -- the set the reference
+    obtains through autograd."""
+
+    @staticmethod
+    def forward(ctx, x1, ell1, x2, ell2, scale):
+        ctx.save_for_backward(x1, ell1, x2, ell2, scale)
+        return gibbs_diag_fwd(x1.detach(), ell1.detach(), x2.detach(), ell2.detach(),
+                              None if scale is None else scale.detach())
+
+    @staticmethod
+    def backward(ctx, G):
+        x1, ell1, x2, ell2, scale = ctx.saved_tensors
+        nd = ctx.needs_input_grad
+        r = gibbs_diag_bwd(x1, ell1, x2, ell2, scale, G=G, need_dx1=nd[0], need_dx2=nd[2],
+                           need_dscale=scale is not None and nd[4])
+        return (r["d_x1"], r["d_ell1"] if nd[1] else None, r["d_x2"], r["d_ell2"] if nd[3] else None,
+                r["d_scale"].reshape(scale.shape) if (scale is not None and nd[4]) else None)
+
+
+class GibbsFullFn(torch.autograd.Function):
+    """Full-matrix Gibbs kernel from packed Sigma; gradients to x1, S1p, x2, S2p, scale (packed-symmetric convention
+    converted so that the returned grad is w.r.t. the PACKED entries: off-diagonals count twice)."""
+
+    @staticmethod
+    def forward(ctx, x1, S1p, x2, S2p, scale, jitter):
+        ctx.save_for_backward(x1, S1p, x2, S2p, scale)
+        ctx.jitter = jitter
+        return gibbs_full_fwd(x1.detach(), S1p.detach(), x2.detach(), S2p.detach(), jitter,
+                              None if scale is None else scale.detach())
+
+    @staticmethod
+    def backward(ctx, G):
+        x1, S1p, x2, S2p, scale = ctx.saved_tensors
+        nd = ctx.needs_input_grad
+        r = gibbs_full_bwd(x1, S1p, x2, S2p, ctx.jitter, scale, G=G, need_dx1=nd[0], need_dx2=nd[2],
+                           need_dscale=scale is not None and nd[4])
+        d = x1.shape[1]
+        mult = _offdiag_multiplier(d, x1.device)
+        return (r["d_x1"], r["d_S1"] * mult if nd[1] else None, r["d_x2"], r["d_S2"] * mult if nd[3] else None,
+                r["d_scale"].reshape(scale.shape) if (scale is not None and nd[4]) else None, None)
+
+
+def _offdiag_multiplier(d, device):
+    iu = torch.triu_indices(d, d, device=device)
+    return torch.where(iu[0] == iu[1], 1.0, 2.0).to(torch.float64)
+
+
+class SigmaFromHFn(torch.autograd.Function):
+    """Packed Sigma(h) (multivariate_gibbs_kernel.py:98).  Incoming grad is w.r.t. packed entries."""
+
+    @staticmethod
+    def forward(ctx, H, Dm):
+        ctx.save_for_backward(H, Dm)
+        return sigma_from_h_fwd(H.detach(), Dm.detach())
+
+    @staticmethod
+    def backward(ctx, dSp):
+        H, Dm = ctx.saved_tensors
+        d = H.shape[1]
+        # kernel expects entries of the symmetric-matrix gradient: packed grad / multiplicity
+        dH, dD = sigma_from_h_bwd(H, Dm, dSp / _offdiag_multiplier(d, H.device), need_dD=ctx.needs_input_grad[1])
+        return dH if ctx.needs_input_grad[0] else None, dD
+
+
+class RbfMatvecFn(torch.autograd.Function):
+    """Matrix-free field interpolation; gradients to z and V (the prior hyper-parameters lam/os/bias are frozen in the
+    reference's experiments, spatial_exp.py:166-167, and get no gradient here)."""
+
+    @staticmethod
+    def forward(ctx, x, z, lam, os, V, bias, apply_exp):
+        out = rbf_matvec_fwd(x.detach(), z.detach(), lam.detach(), None if os is None else os.detach(), V.detach(),
+                             None if bias is None else bias.detach(), apply_exp)
+        ctx.save_for_backward(x, z, lam, os, V, out if apply_exp else None)
+        ctx.apply_exp = apply_exp
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        x, z, lam, os, V, out = ctx.saved_tensors
+        if ctx.apply_exp:
+            dOut = dOut * out
+        dV, dz = rbf_matvec_bwd(x, z, lam, os, V, dOut, need_dz=ctx.needs_input_grad[1])
+        return None, dz, None, None, dV if ctx.needs_input_grad[4] else None, None, None
+
+
+def gibbs_diag(x1, ell1, x2, ell2, scale=None):
+    return GibbsDiagFn.apply(x1, ell1, x2, ell2, scale)
+
+
+def gibbs_full(x1, S1p, x2, S2p, scale=None, jitter=1e-5):
+    return GibbsFullFn.apply(x1, S1p, x2, S2p, scale, jitter)
+
+
+def sigma_from_h(H, Dm):
+    return SigmaFromHFn.apply(H, Dm)
+
+
+def rbf_matvec(x, z, lam, os, V, bias=None, apply_exp=False):
+    return RbfMatvecFn.apply(x, z, lam, os, V, bias, apply_exp)
+
+
+def available() -> bool:
+    import os
+    return os.path.exists(_lib.LIB_PATH)
