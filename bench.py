@@ -1,0 +1,333 @@
+#!/usr/bin/env python3
+"""Headline benchmark: SVGP-Gibbs ELBO steps/s at BASELINE.json config 2 (sparse multivariate Gibbs SVGP, synthetic 3-D
+inputs, N = 2^20, M = 1024 inducing points, global minibatch 65536, fp64), rows of each minibatch sharded over the ranks.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--variant full|diag] [--impl reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py ...
+
+One step = field interpolation -> K(X_B,Z) -> Kzz Cholesky -> whitened predictive mean/variance -> Gaussian E[log-lik] +
+KL -> analytic backward -> ONE NCCL all-reduce of the flat gradient -> Adam.  Prints ONE JSON line.
+`--impl reference` times the reference's CPU path (its pure-PyTorch restatement, oracle/, with autograd; GPyTorch is not
+installable here) on the host cores, on a bounded row sample, scaled to the same metric."""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TOTAL, M_IND, B_GLOBAL, DIM = 1 << 20, 1024, 65536, 3
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def make_params(variant, M, d, seed=173):
+    """Initial parameters per SURVEY.md 8(d) C2 (identical on every rank: generated on CPU from one seed)."""
+    g = torch.Generator().manual_seed(seed)
+    f64 = torch.float64
+    kw = dict(m=1e-3 * torch.randn(M, generator=g, dtype=f64), Ls=torch.eye(M, dtype=f64), outputscale=0.644,
+              noise=0.011)
+    if variant == "diag":
+        kw.update(log_ell_z=math.log(0.3) + 0.1 * torch.randn(d, M, generator=g, dtype=f64),
+                  prior_c=torch.full((d,), math.log(0.3), dtype=f64), prior_os=torch.ones(d, dtype=f64),
+                  prior_lam=torch.full((d, d), 1.3, dtype=f64))
+    else:
+        Dd = torch.randn(d, generator=g, dtype=f64)
+        Dd = torch.sign(Dd) * Dd.abs().clamp_min(0.7)  # 3-D Sigma(h) needs |D_kk| >~ 0.6 to stay PD
+        kw.update(H=torch.randn(M, d, generator=g, dtype=f64), Dm=torch.diag(Dd), row_os=1.0,
+                  row_lam=torch.ones(d, dtype=f64))
+    return kw
+
+
+def make_data(N, d, seed=173):
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(N, d, generator=g, dtype=torch.float64) * 2 - 1
+    y = torch.sin(3 * x[:, 0]) + 0.5 * torch.cos(5 * x[:, 1] * x[:, 2]) + 0.1 * torch.randn(N, generator=g,
+                                                                                          dtype=torch.float64)
+    perm = torch.randperm(N, generator=g)
+    return x, y, perm
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(variant, rows, M, threads, repeats=2):
+    """Seconds for one ELBO forward + autograd backward of the oracle on `rows` minibatch rows (host cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import gibbs_oracle as o
+    from nonstationary_precip_b200.svgp import _inv_softplus
+    torch.set_num_threads(threads)
+    kw = make_params(variant, M, DIM)
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(rows, DIM, generator=g, dtype=torch.float64) * 2 - 1
+    y = torch.sin(3 * x[:, 0]) + 0.1 * torch.randn(rows, generator=g, dtype=torch.float64)
+    Z = torch.rand(M, DIM, generator=g, dtype=torch.float64) * 2 - 1
+    P = dict(Z=Z.clone(), m=kw["m"].clone(), Ls=kw["Ls"].clone(), ro=torch.tensor(_inv_softplus(kw["outputscale"])),
+             rn=torch.tensor(_inv_softplus(kw["noise"] - 1e-4)))
+    if variant == "diag":
+        P["f"] = kw["log_ell_z"].clone()
+        extra = lambda: dict(log_ell_z=P["f"], prior_c=kw["prior_c"], prior_os=kw["prior_os"], prior_lam=kw["prior_lam"])
+    else:
+        P["f"], P["D"] = kw["H"].clone(), kw["Dm"].clone()
+        extra = lambda: dict(H=P["f"], Dm=P["D"], row_os=torch.tensor(1.0, dtype=torch.float64), row_lam=kw["row_lam"])
+    for v in P.values():
+        v.requires_grad_(True)
+    best = float("inf")
+    for it in range(repeats + 1):
+        for v in P.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss = -o.svgp_gibbs_elbo(x, y, N_TOTAL, P["Z"], P["m"], P["Ls"], P["ro"], P["rn"], variant, chunk=2048,
+                                  **extra())
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it > 0:
+            best = min(best, dt)
+    return best
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = args.ref_rows
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = cpu_reference_step_time(args.variant, rows, M_IND, threads, repeats=0 if i else 1)
+        if i >= args.warmup:
+            times.append(t)
+    t_step = sum(times) / len(times) * (B_GLOBAL / rows)
+    val = 1.0 / t_step
+    sample = "%d of %d minibatch rows per step (M=%d), time scaled x%d; fwd+autograd bwd, torch %s CPU fp64" % (
+        rows, B_GLOBAL, M_IND, B_GLOBAL // rows, torch.__version__)
+    line = {"impl": "reference", "metric": "SVGP-Gibbs ELBO steps/s", "value": val, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "BASELINE config 2: sparse multivariate Gibbs SVGP, synthetic 3-D inputs, N=2^20, M=1024, "
+                        "global minibatch 65536, fp64" + ("" if args.variant == "full" else " [diagonal-Gibbs variant]"),
+            "kernel_variant": args.variant, "N": N_TOTAL, "M": M_IND, "global_batch": B_GLOBAL, "d": DIM,
+            "parallelism": "rows of each minibatch sharded over ranks, one NCCL all-reduce of the flat gradient",
+            "l2": "per-step K and T matrices are 512 MiB each (> 126 MB L2), so no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from nonstationary_precip_b200 import ops
+    from nonstationary_precip_b200._lib import check, lib, ptr, stream
+    from nonstationary_precip_b200.svgp import SVGPGibbs
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if rank == 0 and world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    x_h, y_h, perm = make_data(N_TOTAL, DIM)
+    kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_params(args.variant, M_IND, DIM).items()}
+    Z = x_h[perm[:M_IND]].to(dev)
+    model = SVGPGibbs(args.variant, Z, N_TOTAL, **kw)
+    X, Y = x_h.to(dev), y_h.to(dev)  # whole data set resident in HBM (33 MB)
+    Bl = B_GLOBAL // world
+    nb = N_TOTAL // B_GLOBAL
+    all_reduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+
+    def rows(k):
+        lo = (k % nb) * B_GLOBAL + rank * Bl
+        return lo, lo + Bl
+
+    def step_resident(k):
+        lo, hi = rows(k)
+        return model.train_step(X[lo:hi], Y[lo:hi], lr=args.lr, world_size=world, B_global=B_GLOBAL,
+                                all_reduce=all_reduce)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for k in range(args.warmup):
+        step_resident(k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib().npgp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        loss = step_resident(args.warmup + k)
+    ev1.record()
+    barrier()
+    ms = allmax(ev0.elapsed_time(ev1))
+    launches = lib().npgp_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = loss.item()
+
+    # ---- end to end: minibatch from pinned host memory every step, loss read back every step
+    xp, yp = x_h.pin_memory(), y_h.pin_memory()
+    xb = torch.empty(Bl, DIM, dtype=torch.float64, device=dev)
+    yb = torch.empty(Bl, dtype=torch.float64, device=dev)
+
+    def step_e2e(k):
+        lo, hi = rows(k)
+        xb.copy_(xp[lo:hi], non_blocking=True)
+        yb.copy_(yp[lo:hi], non_blocking=True)
+        return model.train_step(xb, yb, lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce).item()
+
+    for k in range(min(2, args.warmup)):
+        step_e2e(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
+    barrier()
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
+
+    # ---- per-kernel evidence for the roofline (CUDA events around the sections of a few extra steps)
+    model.profile = {}
+    for k in range(3):
+        step_resident(k)
+    torch.cuda.synchronize()
+    sec = model.section_ms()
+    model.profile = None
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    peak_tf = 0.0
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(lib().npgp_fp64_peak_probe(1, 148 * 8, 2048, ptr(out), stream()), "probe")
+        b.record()
+        b.synchronize()
+        peak_tf = max(peak_tf, 148 * 8 * 2048 * 8 * 16 * 512 / a.elapsed_time(b) / 1e9)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    rq_tf = 2.0 * Bl * M_IND * M_IND / sec["rowquad"] / 1e9
+    kxz_gbs = 16.0 * Bl * M_IND / (sec["kxz_fwd"] + sec["kxz_bwd"]) / 1e6
+
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        cpu_rows = args.ref_rows
+        t_cpu = cpu_reference_step_time(args.variant, cpu_rows, M_IND, threads) * (B_GLOBAL / cpu_rows) if world == 1 \
+            else None
+        line = {
+            "metric": "SVGP-Gibbs ELBO steps/s", "value": args.steps / (ms / 1e3), "unit": "steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
+                    "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},
+            "roofline": {"bound": "tensor", "kernel": "dgemm_kernel (rowquad T = K C, FP64 DMMA)", "achieved": rq_tf,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": rq_tf / peak_tf, "traffic": None,
+                         "peak_source": "in-run DMMA.8x8x4 probe; MEASURED_PEAKS.json has no FP64 entry "
+                                        "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)"},
+            "roofline_kxz": {"bound": "hbm", "kernel": "gibbs_%s fwd+bwd (K written, T read: 16 B/pair)" % args.variant,
+                             "achieved": kxz_gbs, "peak": hbm, "unit": "GB/s", "frac": kxz_gbs / hbm,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            "sections_ms": {k: round(v, 4) for k, v in sec.items()},
+            "final_loss": final_loss,
+        }
+        if t_cpu is not None:
+            line["cpu_baseline"] = {
+                "value": 1.0 / t_cpu, "unit": "steps/s", "cores": threads, "kind": "port",
+                "sample": "%d of %d minibatch rows (M=%d) fwd+autograd bwd of the oracle, time scaled x%d" % (
+                    cpu_rows, B_GLOBAL, M_IND, B_GLOBAL // cpu_rows)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="full", choices=["full", "diag"])
+    ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--ref-rows", type=int, default=2048, help="minibatch rows the CPU reference processes per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,6 +24,8 @@ typedef struct CUstream_st* npgp_stream_t; /* == cudaStream_t */
 #define NPGP_EWORKSPACE (-3)
 
 int npgp_version(void);
+/* diagnostic: kernels launched through this library so far in this process (bench.py's "gpu_launches") */
+long npgp_launch_count(void);
 
 /* ---- (a) fused Gibbs cross-covariance tiles ------------------------------------------------------------------------
  * Diagonal Gibbs kernel, replaces GibbsKernel.forward (models/gibbs_kernels.py:135-162).
@@ -95,6 +97,25 @@ int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t st
 long npgp_potrf_workspace_bytes(int M);
 int npgp_potrf_inv_lower(int M, double* A, long lda, double* P, long ldp, void* work, long work_bytes, int* info,
                          npgp_stream_t stream);
+
+/* ---- SVGP-Gibbs ELBO step: small kernels (GPyTorch VariationalELBO + GaussianLikelihood.expected_log_prob semantics
+ * as driven by experiments/deepgp_spatial_bench.py:61,84-87) -------------------------------
+ * out[j] += sum_i w_i K[i,j] (w NULL = ones; accumulated): K_zx y of SGPR, K_xz^T g_mu of the ELBO backward. */
+int npgp_colwsum(int n, int M, const double* K, long ldk, const double* w, double* out, npgp_stream_t stream);
+/* out[i] = sum_j A[i,j] v[j] (overwritten): predictive mean K_xz u, P du of the backward. */
+int npgp_gemv_n(int n, int M, const double* A, long lda, const double* v, double* out, npgp_stream_t stream);
+/* Gaussian expected log-likelihood over n rows.  v_i = max(*kdiag + jitter_xx + q_i, min_var);
+ * acc3[0] += sum_i E_q log N(y_i | f_i, *noise); acc3[1] += sum_i ((y_i-mu_i)^2 + v_i); acc3[2] += #rows not clamped;
+ * gmu_i = wscale (y_i-mu_i)/noise, gv_i = -0.5 wscale/noise (0 where clamped); var_out (may be NULL) = v. */
+int npgp_gauss_ell(int n, const double* y, const double* mu, const double* q, const double* kdiag, double jitter_xx,
+                   double min_var, const double* noise, double wscale, double* var_out, double* gmu, double* gv,
+                   double* acc3, npgp_stream_t stream);
+/* X <- alpha * Phi(X): lower triangle, diagonal halved, upper zeroed (Cholesky backward). */
+int npgp_phi_mask(int M, double* X, long ldx, double alpha, npgp_stream_t stream);
+/* Fused Adam over a flat parameter buffer (torch.optim.Adam semantics as used by experiments/spatial_exp.py:193);
+ * g is scaled by gscale first; entries with mask[i] == 0 are frozen (mask may be NULL). */
+int npgp_adam_step(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
+                   double beta1, double beta2, double eps, int step, double gscale, npgp_stream_t stream);
 
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);

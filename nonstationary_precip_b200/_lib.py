@@ -19,6 +19,7 @@ _d = C.c_double
 
 _SIGS = {
     "npgp_version": ([], _i),
+    "npgp_launch_count": ([], _l),
     "npgp_gibbs_diag_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p], _i),
     "npgp_gibbs_diag_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p], _i),
     "npgp_gibbs_full_fwd": ([_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _l, _p, _p, _p], _i),
@@ -34,6 +35,11 @@ _SIGS = {
     "npgp_potrf_workspace_bytes": ([_i], _l),
     "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
+    "npgp_colwsum": ([_i, _i, _p, _l, _p, _p, _p], _i),
+    "npgp_gemv_n": ([_i, _i, _p, _l, _p, _p, _p], _i),
+    "npgp_gauss_ell": ([_i, _p, _p, _p, _p, _d, _d, _p, _d, _p, _p, _p, _p, _p], _i),
+    "npgp_phi_mask": ([_i, _p, _l, _d, _p], _i),
+    "npgp_adam_step": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _i, _d, _p], _i),
 }
 
 _lib = None

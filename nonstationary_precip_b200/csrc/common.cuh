@@ -8,8 +8,12 @@
 #define NPGP_EUNSUPPORTED (-2)
 #define NPGP_EWORKSPACE (-3)  // workspace too small
 
+// diagnostic only: number of kernel launches issued through this library (read by bench.py for "gpu_launches")
+extern "C" long npgp_launch_counter;
+
 #define NPGP_LAUNCH_CHECK()                       \
   do {                                            \
+    ++npgp_launch_counter;                        \
     cudaError_t e__ = cudaGetLastError();         \
     if (e__ != cudaSuccess) return (int)e__;      \
   } while (0)

@@ -1,0 +1,156 @@
+// Small kernels of the SVGP-Gibbs ELBO step: weighted column sums K^T w, the Gaussian expected-log-likelihood
+// reduction with its per-row gradient seeds, the Cholesky-backward mask, and a fused Adam update over the flat
+// parameter buffer.  (VariationalELBO / GaussianLikelihood.expected_log_prob semantics: SURVEY.md Appendix B.4.)
+#include "common.cuh"
+
+namespace npgp {
+
+// out[j] += sum_i w_i K[i,j]   (K is n x M row-major).  Block = 256 columns x row slice; coalesced along j.
+__global__ void __launch_bounds__(256) colwsum_kernel(int n, int M, const double* __restrict__ K, long ldk,
+                                                      const double* __restrict__ w, int rows_per_cta,
+                                                      double* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+  if (j >= M) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int i = r0;
+  for (; i + 3 < r1; i += 4) {
+    a0 = fma(w ? w[i] : 1.0, K[(long)i * ldk + j], a0);
+    a1 = fma(w ? w[i + 1] : 1.0, K[(long)(i + 1) * ldk + j], a1);
+    a2 = fma(w ? w[i + 2] : 1.0, K[(long)(i + 2) * ldk + j], a2);
+    a3 = fma(w ? w[i + 3] : 1.0, K[(long)(i + 3) * ldk + j], a3);
+  }
+  for (; i < r1; ++i) a0 = fma(w ? w[i] : 1.0, K[(long)i * ldk + j], a0);
+  atomicAdd(&out[j], (a0 + a1) + (a2 + a3));
+}
+
+// out[i] = sum_j A[i,j] v[j]  (one warp per row)
+__global__ void __launch_bounds__(256) gemv_n_kernel(int n, int M, const double* __restrict__ A, long lda,
+                                                     const double* __restrict__ v, double* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double a = 0.0;
+  for (int j = lane; j < M; j += 32) a = fma(A[(long)row * lda + j], v[j], a);
+  a = warp_sum(a);
+  if (lane == 0) out[row] = a;
+}
+
+// Gaussian expected log-likelihood over rows and gradient seeds.
+//   v_i = max(kdiag + jitter_xx + q_i, min_var);  ell_i = -0.5 [ ((y-mu)^2 + v)/s2 + log s2 + log 2pi ]
+//   acc[0] += sum ell_i;  acc[1] += sum ((y-mu)^2 + v)   (for d/d s2);  acc[2] += #unclamped rows
+//   gmu_i = wscale (y-mu)/s2;   gv_i = -0.5 wscale / s2 (0 where clamped)
+__global__ void __launch_bounds__(256) gauss_ell_kernel(int n, const double* __restrict__ y,
+                                                        const double* __restrict__ mu, const double* __restrict__ q,
+                                                        const double* __restrict__ kdiag_p, double jitter_xx,
+                                                        double min_var, const double* __restrict__ noise_p,
+                                                        double wscale, double* __restrict__ var_out,
+                                                        double* __restrict__ gmu, double* __restrict__ gv,
+                                                        double* __restrict__ acc) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const double s2 = *noise_p, kd = *kdiag_p;
+  double e = 0.0, r2v = 0.0, cnt = 0.0;
+  if (i < n) {
+    double v = kd + jitter_xx + q[i];
+    const bool clamped = v < min_var;
+    if (clamped) v = min_var;
+    const double r = y[i] - mu[i];
+    e = -0.5 * ((r * r + v) / s2 + log(s2) + 1.8378770664093453);
+    r2v = r * r + v;
+    cnt = clamped ? 0.0 : 1.0;
+    if (var_out) var_out[i] = v;
+    gmu[i] = wscale * r / s2;
+    gv[i] = clamped ? 0.0 : -0.5 * wscale / s2;
+  }
+  double t = block_sum(e, red);
+  if (threadIdx.x == 0) atomicAdd(&acc[0], t);
+  t = block_sum(r2v, red);
+  if (threadIdx.x == 0) atomicAdd(&acc[1], t);
+  t = block_sum(cnt, red);
+  if (threadIdx.x == 0) atomicAdd(&acc[2], t);
+}
+
+// Phi(X): lower triangle with halved diagonal, in place (Cholesky backward, Murray 2016), scaled by alpha
+__global__ void phi_mask_kernel(int M, double* X, long ldx, double alpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r >= M || c >= M) return;
+  double* p = X + (long)r * ldx + c;
+  *p = (c < r) ? alpha * *p : ((c == r) ? 0.5 * alpha * *p : 0.0);
+}
+
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad), maximize=false:  p -= lr * mhat / (sqrt(vhat) + eps)
+__global__ void adam_kernel(long n, double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
+                            double* __restrict__ v, const double* __restrict__ mask, double lr, double b1, double b2,
+                            double eps, double bc1, double bc2, double gscale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask && mask[i] == 0.0) return;
+  const double gi = gscale * g[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / bc1) / (sqrt(vi / bc2) + eps);
+}
+
+}  // namespace npgp
+
+using namespace npgp;
+
+extern "C" int npgp_colwsum(int n, int M, const double* K, long ldk, const double* w, double* out,
+                            cudaStream_t stream) {
+  if (n < 0 || M < 0) return NPGP_EINVAL;
+  if (n == 0 || M == 0) return NPGP_OK;
+  if (!K || !out) return NPGP_EINVAL;
+  const int cb = ceil_div(M, 256);
+  long row_ctas = (kNumSMs * 8 + cb - 1) / cb;
+  long rpc = (n + row_ctas - 1) / row_ctas;
+  if (rpc < 64) rpc = 64;
+  dim3 grid(cb, ceil_div(n, rpc));
+  colwsum_kernel<<<grid, 256, 0, stream>>>(n, M, K, ldk, w, (int)rpc, out);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+extern "C" int npgp_gemv_n(int n, int M, const double* A, long lda, const double* v, double* out, cudaStream_t stream) {
+  if (n < 0 || M < 0) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!A || !v || !out) return NPGP_EINVAL;
+  gemv_n_kernel<<<ceil_div(n, 8), 256, 0, stream>>>(n, M, A, lda, v, out);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+extern "C" int npgp_gauss_ell(int n, const double* y, const double* mu, const double* q, const double* kdiag,
+                              double jitter_xx, double min_var, const double* noise, double wscale, double* var_out,
+                              double* gmu, double* gv, double* acc3, cudaStream_t stream) {
+  if (n < 0) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!y || !mu || !q || !kdiag || !noise || !gmu || !gv || !acc3) return NPGP_EINVAL;
+  gauss_ell_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n, y, mu, q, kdiag, jitter_xx, min_var, noise, wscale, var_out,
+                                                         gmu, gv, acc3);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+extern "C" int npgp_phi_mask(int M, double* X, long ldx, double alpha, cudaStream_t stream) {
+  if (M < 0 || (M > 0 && !X)) return NPGP_EINVAL;
+  if (M == 0) return NPGP_OK;
+  dim3 blk(32, 8), grd(ceil_div(M, 32), ceil_div(M, 8));
+  phi_mask_kernel<<<grd, blk, 0, stream>>>(M, X, ldx, alpha);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+extern "C" int npgp_adam_step(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
+                              double beta1, double beta2, double eps, int step, double gscale, cudaStream_t stream) {
+  if (n < 0 || step < 1) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!p || !g || !m || !v) return NPGP_EINVAL;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, p, g, m, v, mask, lr, beta1, beta2, eps, bc1, bc2,
+                                                               gscale);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}

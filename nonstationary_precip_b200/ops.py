@@ -189,6 +189,46 @@ def potrf_inv(A, overwrite=False):
     return L, P, info
 
 
+def colwsum(K, w=None, out=None):
+    """out[j] (+)= sum_i w_i K[i,j]."""
+    n, M = K.shape
+    if out is None:
+        out = torch.zeros(M, dtype=torch.float64, device=K.device)
+    check(lib().npgp_colwsum(n, M, ptr(K), K.stride(0), ptr(_c(w)), ptr(out), stream()), "npgp_colwsum")
+    return out
+
+
+def gemv_n(A, v):
+    """A @ v (one warp per row)."""
+    n, M = A.shape
+    out = torch.empty(n, dtype=torch.float64, device=A.device)
+    check(lib().npgp_gemv_n(n, M, ptr(A), A.stride(0), ptr(_c(v)), ptr(out), stream()), "npgp_gemv_n")
+    return out
+
+
+def gauss_ell(y, mu, q, kdiag, noise, jitter_xx=1e-4, min_var=1e-6, wscale=1.0, want_var=False):
+    """Gaussian expected log-lik sums + gradient seeds; kdiag, noise are device scalars.  Returns (acc3, gmu, gv, var)."""
+    n = y.shape[0]
+    z = lambda *s: torch.empty(*s, dtype=torch.float64, device=y.device)
+    gmu, gv = z(n), z(n)
+    var = z(n) if want_var else None
+    acc = torch.zeros(3, dtype=torch.float64, device=y.device)
+    check(lib().npgp_gauss_ell(n, ptr(_c(y)), ptr(mu), ptr(q), ptr(kdiag), float(jitter_xx), float(min_var), ptr(noise),
+                               float(wscale), ptr(var), ptr(gmu), ptr(gv), ptr(acc), stream()), "npgp_gauss_ell")
+    return acc, gmu, gv, var
+
+
+def phi_mask_(X, alpha=1.0):
+    check(lib().npgp_phi_mask(X.shape[0], ptr(X), X.stride(0), float(alpha), stream()), "npgp_phi_mask")
+    return X
+
+
+def adam_step_(p, g, m, v, step, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, mask=None):
+    check(lib().npgp_adam_step(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), ptr(mask), float(lr), float(beta1),
+                               float(beta2), float(eps), int(step), float(gscale), stream()), "npgp_adam_step")
+    return p
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # autograd Functions (analytic backward kernels)
 # ----------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,356 @@
+"""Whitened SVGP with a Gibbs prior covariance whose latent lengthscale field lives at the inducing points -- the
+"SVGP-Gibbs ELBO" of BASELINE.json (composition defined in SURVEY.md Appendix B from the reference's parts:
+InducingGibbsKernel's field handling, models/gibbs_kernels.py:210-223; the multivariate kernels,
+models/sparse_multivariate_gibbs_kernel.py:67-154; GPyTorch's whitened VariationalStrategy + VariationalELBO as driven
+by models/dgps.py:25-35 and experiments/deepgp_spatial_bench.py:61,84-87).
+
+One training step = field interpolation -> K(X_B,Z), Kzz -> Cholesky -> whitened predictive mean/variance ->
+Gaussian E[log-lik] + KL -> ANALYTIC backward (no autograd graph) -> one all-reduce of the flat gradient -> Adam.
+Every O(B*M), O(B*M^2) and O(M^3) operation is a hand-written kernel behind the C ABI (``ops``); torch is used for
+device memory, streams, O(M^2)/O(B) elementwise glue and ``torch.distributed``.
+
+Gradient chain used below (E = S - I, S = Ls Ls^T, P = L^-1, L = chol(Kzz + jitter I), u = P^T m, C = P^T E P):
+    mu = K u,  v = s + jitter_xx + rowdot(K C, K)
+    G  = dELBO/dK   = g_mu u^T + 2 diag(g_v) (K C)            (formed inside the Gibbs backward kernel)
+    du = K^T g_mu,  dC = K^T diag(g_v) K,  dm = P du,  dE = P dC P^T,  dLs = tril(2 dE Ls)
+    dKzz = sym( P^T Phi(-(2 E dE + m dm^T)) P )               (Cholesky + inverse backward folded: L^T dL = -dP P^T)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops as _cuda_ops
+
+LOG2PI = math.log(2.0 * math.pi)
+
+
+def _softplus(x):
+    return torch.nn.functional.softplus(x)
+
+
+def _inv_softplus(v: float) -> float:
+    return v + math.log(-math.expm1(-v))
+
+
+class _Section:
+    """CUDA-event bracket around a named part of the step (only when model.profile is set; never under graph capture)."""
+
+    def __init__(self, store, name):
+        self.store, self.name = store, name
+
+    def __enter__(self):
+        if self.store is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.store is not None:
+            self.b.record()
+            self.store.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+class SVGPGibbs:
+    """variant = 'diag' (GibbsKernel, log-normal field) or 'full' (multivariate Gibbs, matrix-valued field H, D)."""
+
+    def __init__(self, variant: str, Z: torch.Tensor, N_total: int, *, log_ell_z=None, prior_c=None, prior_os=None,
+                 prior_lam=None, H=None, Dm=None, row_os=None, row_lam=None, m=None, Ls=None, outputscale=0.644,
+                 noise=0.011, jitter_zz=1e-6, jitter_xx=1e-4, kernel_jitter=1e-5, learn_inducing_locations=True,
+                 include_prior=True, ops=None):
+        assert variant in ("diag", "full")
+        self.o = ops if ops is not None else _cuda_ops
+        self.variant, self.N = variant, int(N_total)
+        self.dev = Z.device
+        self.M, self.d = Z.shape
+        M, d = self.M, self.d
+        self.jitter_zz, self.jitter_xx, self.kernel_jitter = jitter_zz, jitter_xx, kernel_jitter
+        self.learn_z, self.include_prior = learn_inducing_locations, include_prior
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        # ---- flat parameter / gradient buffers with named views
+        shapes = [("Z", (M, d))]
+        shapes += [("log_ell_z", (d, M))] if variant == "diag" else [("H", (M, d)), ("D", (d, d))]
+        shapes += [("m", (M,)), ("Ls", (M, M)), ("raw_outputscale", (1,)), ("raw_noise", (1,))]
+        self.shapes = shapes
+        n = sum(int(torch.tensor(s).prod()) for _, s in shapes)
+        n_pad = (n + 1) // 2 * 2
+        self.theta = torch.zeros(n_pad, **f64)
+        self.grad = torch.zeros(n_pad + 2, **f64)  # [-2]: loss, [-1]: spare -> one all-reduce carries everything
+        self.adam_m, self.adam_v = torch.zeros(n_pad, **f64), torch.zeros(n_pad, **f64)
+        self.mask = torch.ones(n_pad, **f64)
+        self.p, self.g, self._mask_views = {}, {}, {}
+        off = 0
+        for name, shp in shapes:
+            k = int(torch.tensor(shp).prod())
+            self.p[name] = self.theta[off:off + k].view(*shp)
+            self.g[name] = self.grad[off:off + k].view(*shp)
+            self._mask_views[name] = self.mask[off:off + k].view(*shp)
+            off += k
+        self.n_params = n
+        self.p["Z"].copy_(Z)
+        if variant == "diag":
+            self.p["log_ell_z"].copy_(log_ell_z)
+            self.prior_c, self.prior_os, self.prior_lam = (t.to(**f64).contiguous() for t in (prior_c, prior_os, prior_lam))
+        else:
+            self.p["H"].copy_(H)
+            self.p["D"].copy_(Dm)
+            self.row_os = torch.as_tensor(row_os, **f64).reshape(1).contiguous()
+            self.row_lam = torch.as_tensor(row_lam, **f64).reshape(1, d).contiguous()
+            if not torch.allclose(Dm * Dm, (Dm * Dm).T):
+                raise ValueError("D o D must be symmetric (the reference initialises D diagonal)")
+        self.p["m"].copy_(m if m is not None else torch.zeros(M))
+        self.p["Ls"].copy_(Ls if Ls is not None else torch.eye(M))
+        self.p["raw_outputscale"].fill_(_inv_softplus(outputscale))
+        self.p["raw_noise"].fill_(_inv_softplus(noise - 1e-4))
+        self._mask_views["Ls"].copy_(torch.tril(torch.ones(M, M)))
+        if not learn_inducing_locations:
+            self._mask_views["Z"].zero_()
+        self.eye = torch.eye(M, **f64)
+        self.step_count = 0
+        self.profile = None  # set to a dict to collect per-section CUDA-event pairs
+
+    def _sec(self, name):
+        return _Section(self.profile, name)
+
+    def section_ms(self):
+        """Mean milliseconds per section from the collected events (call after torch.cuda.synchronize())."""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.profile or {}).items()}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def freeze(self, name):
+        self._mask_views[name].zero_()
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.p.items()}
+
+    def _bcast_ell(self, lam_row, n):
+        return lam_row.reshape(-1, 1).expand(self.d, n).contiguous()
+
+    def _kernel_fwd(self, x1, f1, x2, f2, scale, u=None, out=None):
+        if self.variant == "diag":
+            return self.o.gibbs_diag_fwd(x1, f1, x2, f2, scale, u=u, out=out)
+        return self.o.gibbs_full_fwd(x1, f1, x2, f2, self.kernel_jitter, scale, u=u, out=out)
+
+    def _kernel_bwd(self, x1, f1, x2, f2, scale, **kw):
+        if self.variant == "diag":
+            r = self.o.gibbs_diag_bwd(x1, f1, x2, f2, scale, **kw)
+            return r["d_ell1"], r["d_ell2"], r["d_x1"], r["d_x2"], r["d_scale"]
+        r = self.o.gibbs_full_bwd(x1, f1, x2, f2, self.kernel_jitter, scale, **kw)
+        return r["d_S1"], r["d_S2"], r["d_x1"], r["d_x2"], r["d_scale"]
+
+    def _solve_spd(self, P, rhs):
+        """K^-1 rhs with K = L L^T, P = L^-1.  rhs (M,) or (M,k)."""
+        o = self.o
+        if rhs.dim() == 1:
+            return o.colwsum(P, w=o.gemv_n(P, rhs))
+        k = rhs.shape[1]
+        kp = max(2, (k + 1) // 2 * 2)
+        R = torch.zeros(self.M, kp, dtype=torch.float64, device=self.dev)
+        R[:, :k] = rhs
+        T = o.dgemm(P, R, tri_a=1)
+        return o.dgemm(P, T, transA=True, tri_a=2)[:, :k].contiguous()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _field_forward(self, x):
+        """Latent field at Z and interpolated to the rows x.  Returns (fz, fx, cache)."""
+        o, p, M, d = self.o, self.p, self.M, self.d
+        Z = p["Z"]
+        c = {}
+        if self.variant == "diag":
+            ell_z = torch.exp(p["log_ell_z"])
+            alphas, Ps, Linvdiag = [], [], []
+            for b in range(d):
+                lamb = self._bcast_ell(self.prior_lam[b], M)
+                Kp = o.gibbs_diag_fwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1])
+                Kp.diagonal().add_(1e-4)
+                Lb, Pb, _ = o.potrf_inv(Kp, overwrite=True)
+                alphas.append(self._solve_spd(Pb, p["log_ell_z"][b] - self.prior_c[b]))
+                Ps.append(Pb)
+                Linvdiag.append(torch.diagonal(Lb).clone())
+            alpha = torch.stack(alphas)  # (D,M)
+            ell_x = o.rbf_matvec_fwd(x, Z, self.prior_lam, self.prior_os, alpha.unsqueeze(-1), bias=self.prior_c,
+                                     apply_exp=True).squeeze(-1)
+            c.update(alpha=alpha, Ps=Ps, Ldiag=Linvdiag, ell_z=ell_z, ell_x=ell_x)
+            return ell_z, ell_x, c
+        Sz = o.sigma_from_h_fwd(p["H"], p["D"])
+        lamr = self._bcast_ell(self.row_lam[0], M)
+        Kr = o.gibbs_diag_fwd(Z, lamr, Z, lamr, self.row_os)
+        Kr.diagonal().add_(1e-5)
+        _, Pr, _ = o.potrf_inv(Kr, overwrite=True)
+        W = self._solve_spd(Pr, p["H"])  # (M,d)
+        Hx = o.rbf_matvec_fwd(x, Z, self.row_lam, self.row_os, W.unsqueeze(0))[0]  # (B,d)
+        Sx = o.sigma_from_h_fwd(Hx, p["D"])
+        c.update(Pr=Pr, W=W, Hx=Hx, lamr=lamr)
+        return Sz, Sx, c
+
+    def _zz_forward(self, fz, s):
+        o, p, M = self.o, self.p, self.M
+        Kzz = self._kernel_fwd(p["Z"], fz, p["Z"], fz, s)
+        Kzz.diagonal().add_(self.jitter_zz)
+        L, P, info = o.potrf_inv(Kzz, overwrite=True)
+        Ls = torch.tril(p["Ls"])
+        u = o.colwsum(P, w=p["m"])  # P^T m
+        E = o.dgemm(Ls, Ls, transB=True, tri_a=1, tri_b=2) - self.eye
+        EP = o.dgemm(E, P, tri_b=1)
+        C = o.dgemm(P, EP, transA=True, tri_a=2)
+        return dict(L=L, P=P, info=info, Ls=Ls, u=u, E=E, C=C)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def loss_and_grad(self, xb, yb, world_size: int = 1, B_global: Optional[int] = None):
+        """Fills self.grad with d(-ELBO)/d(theta) for this rank's rows and returns this rank's share of -ELBO
+        (also stored in self.grad[-2]); summing over ranks (one all-reduce of self.grad) gives the global values."""
+        o, p, g, M, d = self.o, self.p, self.g, self.M, self.d
+        Z = p["Z"]
+        Bl = xb.shape[0]
+        Bg = B_global if B_global is not None else Bl * world_size
+        rep = 1.0 / world_size  # weight of the replicated (KL / prior) terms on this rank
+        s = _softplus(p["raw_outputscale"])
+        noise = 1e-4 + _softplus(p["raw_noise"])
+        self.grad.zero_()
+
+        with self._sec("field_fwd"):
+            fz, fx, fc = self._field_forward(xb)
+        with self._sec("zz_fwd(potrf+M^3)"):
+            zz = self._zz_forward(fz, s)
+        P, u, E, C, Ls = zz["P"], zz["u"], zz["E"], zz["C"], zz["Ls"]
+
+        # ---- data pass: K(X_B, Z) (+ mean), variance quadratic form, expected log-lik
+        with self._sec("kxz_fwd"):
+            K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
+        with self._sec("rowquad"):
+            T, q = o.rowquad(K, C)
+        acc, gmu, gv, _ = o.gauss_ell(yb, mu, q, s, noise, self.jitter_xx, 1e-6, 1.0 / Bg)
+        ell = acc[0] / Bg
+
+        # ---- KL and prior (replicated terms)
+        m = p["m"]
+        dLs_diag = torch.diagonal(Ls)
+        kl = 0.5 * ((Ls * Ls).sum() + (m * m).sum() - M - torch.log(dLs_diag * dLs_diag).sum())
+        lp = torch.zeros((), dtype=torch.float64, device=self.dev)
+        if self.include_prior and self.variant == "diag":
+            for b in range(d):
+                r_b = p["log_ell_z"][b] - self.prior_c[b]
+                lp = lp + (-0.5 * (r_b * fc["alpha"][b]).sum() - torch.log(fc["Ldiag"][b]).sum()
+                           - 0.5 * M * LOG2PI) / M
+        elbo_local = ell + rep * (-kl + lp) / self.N
+
+        # ---- backward of the data term through K(X_B, Z)
+        with self._sec("kxz_bwd"):
+            dfx, dfz, _, dZ, ds = self._kernel_bwd(xb, fx, Z, fz, s, G=T, rowscale=2.0 * gv, rowvec=gmu, colvec=u,
+                                                   need_dx2=self.learn_z, need_dscale=True)
+        with self._sec("colwsum"):
+            du = o.colwsum(K, w=gmu)
+        with self._sec("wsyrk"):
+            dC = o.wsyrk(K, w=gv)
+        ds = ds + gv.sum()  # v = s + ...
+        sec_m3 = self._sec("m3_bwd+kzz_bwd+field_bwd")
+        sec_m3.__enter__()
+
+        # ---- O(M^3) backward: u, C -> m, Ls, Kzz
+        dm = o.gemv_n(P, du)
+        dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
+        X = o.dgemm(E, dE, alpha=2.0)
+        X.addr_(m, dm)
+        o.phi_mask_(X, -1.0)
+        dK = o.dgemm(o.dgemm(P, X, transA=True, tri_a=2, tri_b=1), P, tri_b=1)
+        dKzz = 0.5 * (dK + dK.T)
+        dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
+        g["m"].copy_(-(dm - rep * m / self.N))
+        g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
+
+        dfz1, dfz2, dZ1, dZ2, ds2 = self._kernel_bwd(Z, fz, Z, fz, s, G=dKzz, need_dx1=self.learn_z,
+                                                     need_dx2=self.learn_z, need_dscale=True)
+        dfz = dfz + dfz1 + dfz2
+        ds = ds + ds2
+        gZ = torch.zeros_like(Z)
+        if self.learn_z:
+            gZ += dZ + dZ1 + dZ2
+
+        # ---- backward through the field interpolation
+        if self.variant == "diag":
+            alpha, ell_x, ell_z = fc["alpha"], fc["ell_x"], fc["ell_z"]
+            dlog = (dfx * ell_x).unsqueeze(-1)
+            dalpha, dZf = o.rbf_matvec_bwd(xb, Z, self.prior_lam, self.prior_os, alpha.unsqueeze(-1), dlog,
+                                           need_dz=self.learn_z)
+            g_logell = dfz * ell_z
+            for b in range(d):
+                Pb = fc["Ps"][b]
+                beta = self._solve_spd(Pb, dalpha[b, :, 0])
+                g_logell[b] += beta
+                pw = rep / (self.N * M) if self.include_prior else 0.0
+                if self.include_prior:
+                    g_logell[b] -= pw * alpha[b]
+                if self.learn_z:
+                    lamb = self._bcast_ell(self.prior_lam[b], M)
+                    # dELBO/dKp_b = -beta alpha^T  (+ prior: pw (0.5 alpha alpha^T - 0.5 Kp^-1))
+                    Gm = rs = None
+                    rv, cv = -beta, alpha[b]
+                    if self.include_prior:
+                        Gm = o.dgemm(Pb, Pb, transA=True, alpha=-0.5 * pw, tri_a=2, tri_b=1)
+                        rv = rv + 0.5 * pw * alpha[b]
+                    r = o.gibbs_diag_bwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1], G=Gm, rowscale=rs, rowvec=rv,
+                                         colvec=cv, need_dx1=True, need_dx2=True)
+                    gZ += r["d_x1"] + r["d_x2"]
+            if self.learn_z:
+                gZ += dZf
+            g["log_ell_z"].copy_(-g_logell)
+        else:
+            dHx, dD1 = o.sigma_from_h_bwd(fc["Hx"], p["D"], dfx)
+            dW, dZf = o.rbf_matvec_bwd(xb, Z, self.row_lam, self.row_os, fc["W"].unsqueeze(0), dHx.unsqueeze(0),
+                                       need_dz=self.learn_z)
+            beta = self._solve_spd(fc["Pr"], dW[0])  # (M,d) = Kr^-1 dW
+            dHz, dD2 = o.sigma_from_h_bwd(p["H"], p["D"], dfz)
+            g["H"].copy_(-(beta + dHz))
+            g["D"].copy_(-(dD1 + dD2))
+            if self.learn_z:
+                kp = 4
+                b4 = torch.zeros(M, kp, dtype=torch.float64, device=self.dev)
+                w4 = torch.zeros(M, kp, dtype=torch.float64, device=self.dev)
+                b4[:, :d], w4[:, :d] = beta, fc["W"]
+                Gk = o.dgemm(b4, w4, transB=True, alpha=-1.0)  # dELBO/dKr = -beta W^T
+                r = o.gibbs_diag_bwd(Z, fc["lamr"], Z, fc["lamr"], self.row_os, G=Gk, need_dx1=True, need_dx2=True)
+                gZ += dZf + r["d_x1"] + r["d_x2"]
+        g["Z"].copy_(-gZ)
+        g["raw_outputscale"].copy_(-(ds * torch.sigmoid(p["raw_outputscale"])).reshape(1))
+        dnoise = (0.5 / Bg) * (acc[1] / (noise * noise) - Bl / noise)
+        g["raw_noise"].copy_(-(dnoise * torch.sigmoid(p["raw_noise"])).reshape(1))
+        self.grad[-2] = -elbo_local.reshape(())
+        sec_m3.__exit__()
+        self.last = dict(info=zz["info"], ell=ell, kl=kl, log_prior=lp, mu=mu, q=q)
+        return self.grad[-2]
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def adam_step(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.step_count += 1
+        self.o.adam_step_(self.theta, self.grad[:self.theta.numel()], self.adam_m, self.adam_v, self.step_count, lr,
+                          beta1, beta2, eps, 1.0, self.mask)
+
+    def train_step(self, xb, yb, lr=0.01, world_size=1, B_global=None, all_reduce=None):
+        """loss_and_grad -> (all-reduce of the flat gradient) -> Adam.  Returns the (global) loss as a device scalar."""
+        self.loss_and_grad(xb, yb, world_size, B_global)
+        if all_reduce is not None:
+            all_reduce(self.grad)
+        self.adam_step(lr)
+        return self.grad[-2]
+
+    @torch.no_grad()
+    def predict(self, xs, chunk: int = 1 << 18):
+        """Posterior marginal mean and variance of f at xs (rows can be sharded across ranks by the caller)."""
+        o, p = self.o, self.p
+        s = _softplus(p["raw_outputscale"])
+        means, variances = [], []
+        zz = None
+        for lo in range(0, xs.shape[0], chunk):
+            xc = xs[lo:lo + chunk].contiguous()
+            fz, fx, _ = self._field_forward(xc)
+            if zz is None:
+                zz = self._zz_forward(fz, s)
+            K, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"])
+            _, q = o.rowquad(K, zz["C"])
+            means.append(mu)
+            variances.append((s + self.jitter_xx + q).clamp_min(1e-6))
+        return torch.cat(means), torch.cat(variances)
