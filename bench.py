@@ -134,7 +134,7 @@ def cpu_reference_step_time(variant, rows, M, threads, repeats=2):
                                   **extra())
         loss.backward()
         dt = time.perf_counter() - t0
-        if it > 0:
+        if it > 0 or repeats == 0:
             best = min(best, dt)
     return best
 
@@ -207,10 +207,21 @@ def run_ours(args):
         lo = (k % nb) * B_GLOBAL + rank * Bl
         return lo, lo + Bl
 
+    launches_per_replay = 0
+    if args.exec == "graph":
+        c0 = lib().npgp_launch_count()
+        model.capture(Bl, world, B_GLOBAL, lr=args.lr)
+        # capture() runs the step 3 times (2 warm-ups + the captured one); the captured graph holds one step's launches
+        launches_per_replay = (lib().npgp_launch_count() - c0) // 3
+
+    def train(xs, ys):
+        if args.exec == "graph":
+            return model.train_step_graph(xs, ys, all_reduce=all_reduce)
+        return model.train_step(xs, ys, lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce)
+
     def step_resident(k):
         lo, hi = rows(k)
-        return model.train_step(X[lo:hi], Y[lo:hi], lr=args.lr, world_size=world, B_global=B_GLOBAL,
-                                all_reduce=all_reduce)
+        return train(X[lo:hi], Y[lo:hi])
 
     def barrier():
         if world > 1:
@@ -232,7 +243,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = allmax(ev0.elapsed_time(ev1))
-    launches = lib().npgp_launch_count() - l0
+    launches = lib().npgp_launch_count() - l0 + launches_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else None
     final_loss = loss.item()
 
@@ -243,9 +254,11 @@ def run_ours(args):
 
     def step_e2e(k):
         lo, hi = rows(k)
+        if args.exec == "graph":  # train_step_graph copies host -> static device buffers itself
+            return train(xp[lo:hi], yp[lo:hi]).item()
         xb.copy_(xp[lo:hi], non_blocking=True)
         yb.copy_(yp[lo:hi], non_blocking=True)
-        return model.train_step(xb, yb, lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce).item()
+        return train(xb, yb).item()
 
     for k in range(min(2, args.warmup)):
         step_e2e(k)
@@ -258,8 +271,11 @@ def run_ours(args):
 
     # ---- per-kernel evidence for the roofline (CUDA events around the sections of a few extra steps)
     model.profile = {}
-    for k in range(3):
-        step_resident(k)
+    for k in range(3):  # eager, one stream, so that the CUDA-event brackets see each section alone
+        lo, hi = rows(k)
+        model.overlap = False
+        model.train_step(X[lo:hi], Y[lo:hi], lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce)
+        model.overlap = True
     torch.cuda.synchronize()
     sec = model.section_ms()
     model.profile = None
@@ -290,7 +306,8 @@ def run_ours(args):
             "metric": "SVGP-Gibbs ELBO steps/s", "value": args.steps / (ms / 1e3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "config": dict(workload_config(args), exec="cuda_graph + 2 streams" if args.exec == "graph" else "eager"),
+            "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},
             "roofline": {"bound": "tensor", "kernel": "dgemm_kernel (rowquad T = K C, FP64 DMMA)", "achieved": rq_tf,
@@ -321,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="full", choices=["full", "diag"])
     ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--exec", default="graph", choices=["graph", "eager"],
+                    help="replay the step as a captured CUDA graph (default) or launch it eagerly")
     ap.add_argument("--ref-rows", type=int, default=2048, help="minibatch rows the CPU reference processes per step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -117,6 +117,11 @@ int npgp_phi_mask(int M, double* X, long ldx, double alpha, npgp_stream_t stream
 int npgp_adam_step(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
                    double beta1, double beta2, double eps, int step, double gscale, npgp_stream_t stream);
 
+/* Same update with the step counter kept on the device (step_dev[0] = steps taken so far, incremented here), so that a
+ * captured CUDA graph of the training step replays with the correct bias correction. */
+int npgp_adam_step_dev(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
+                       double beta1, double beta2, double eps, double* step_dev, double gscale, npgp_stream_t stream);
+
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 

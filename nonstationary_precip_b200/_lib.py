@@ -40,6 +40,7 @@ _SIGS = {
     "npgp_gauss_ell": ([_i, _p, _p, _p, _p, _d, _d, _p, _d, _p, _p, _p, _p, _p], _i),
     "npgp_phi_mask": ([_i, _p, _l, _d, _p], _i),
     "npgp_adam_step": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _i, _d, _p], _i),
+    "npgp_adam_step_dev": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _p, _d, _p], _i),
 }
 
 _lib = None

@@ -1,136 +1,376 @@
 // Blocked FP64 Cholesky of the M x M inducing covariance and the inverse of its factor, M up to a few thousand.
 //
-//   npgp_potrf_inv_lower:  A = L L^T (in place, strict upper triangle zeroed),  P = L^-1 (lower, upper zeroed),
+//   npgp_potrf_inv_lower:  A = L L^T (L returned in A, strict upper triangle zero),  P = L^-1 (lower),
 //                          info = 0 or (1-based) index of the first non-positive pivot (LAPACK convention) so the
 //                          host can reproduce psd_safe_cholesky's jitter ladder.
 //
 // Replaces psd_safe_cholesky + triangular_solve(eye, chol) (reference models/gibbs_kernels.py:197-208) and the
 // Cholesky inside GPyTorch's VariationalStrategy (models/dgps.py:29-33).
 //
-// Right-looking blocked algorithm, NB = 64: the diagonal block is factored AND inverted by one CTA in shared memory;
-// the panel solve is then a GEMM with the inverted block, the trailing update a lower-triangular rank-64 DMMA update.
-// L^-1 is assembled afterwards by recursive doubling:  inv([[L11,0],[L21,L22]]) = [[P11,0],[-P22 L21 P11, P22]],
-// i.e. two DMMA GEMMs per block pair and level.
+// The factorisation is latency bound (M^3/3 flops is nothing; the critical path is M/64 dependent panel steps), so the
+// design minimises the number and the length of dependent launches:
+//   * ONE kernel per 64-column panel step j.  The CTA that owns trailing tile (i,k) recomputes the two panel tiles it
+//     needs (L_ij = A_ij P_jj^T, L_kj = A_kj P_jj^T: redundant 64^3 DMMA work instead of a separate TRSM launch and a
+//     grid-wide dependency), applies A_ik -= L_ij L_kj^T, and the CTA of tile (j+1,j+1) goes on to factor AND invert the
+//     freshly updated diagonal block, so the next step can start as soon as this kernel retires (look-ahead of 1).
+//   * The 64x64 diagonal block is factored by 64 threads that hold one matrix row each in registers (fully unrolled
+//     right-looking elimination, one rsqrt per pivot, column broadcast through shared memory, two 64-thread named
+//     barriers per column) and inverted column-per-thread by forward substitution.
+//   * L^-1 is assembled by recursive doubling, inv([[L11,0],[L21,L22]]) = [[P11,0],[-P22 L21 P11, P22]]: two batched
+//     kernels per level (all block pairs of a level in one launch), skipping the structurally zero blocks.
+// All tile products run on the FP64 tensor pipe (DMMA.8x8x4).
 #include "common.cuh"
 
 namespace npgp {
 
-int dgemm_impl(int transA, int transB, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
-               long ldb, double beta, double* C, long ldc, int tri_a, int tri_b, int out_tri, cudaStream_t st);
+constexpr int TB = 64;    // tile edge
+constexpr int TLD = 68;   // shared-memory leading dimension (= 4 mod 16: conflict-free fragment loads)
+constexpr int CT = 256;   // threads per CTA (8 warps, warp tile 16 x 32)
+constexpr int TILE_SMEM = TB * TLD;  // doubles
 
-constexpr int NB = 64;
-constexpr int LDB = NB + 1;
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
-// One CTA (256 threads).  A11 (nb x nb at A, leading dim lda) -> L11 written back (upper zeroed); inverse to Pd (ldp).
-__global__ void __launch_bounds__(256) potrf_diag_kernel(int nb, double* __restrict__ A, long lda,
-                                                         double* __restrict__ Pd, long ldp, int global_offset,
-                                                         int* __restrict__ info) {
-  extern __shared__ double dyn_smem[];
-  double(*s)[LDB] = reinterpret_cast<double(*)[LDB]>(dyn_smem);
-  double(*x)[LDB] = reinterpret_cast<double(*)[LDB]>(dyn_smem + NB * LDB);
-  const int tid = threadIdx.x;
-  for (int t = tid; t < NB * NB; t += 256) {
-    const int r = t / NB, c = t % NB;
-    s[r][c] = (r < nb && c <= r) ? A[(long)r * lda + c] : ((r == c) ? 1.0 : 0.0);
-    x[r][c] = 0.0;
+struct WarpPos {
+  int wm0, wn0, g, t4;
+  __device__ WarpPos() {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    wm0 = (w >> 1) * 16;
+    wn0 = (w & 1) * 32;
+    g = lane >> 2;
+    t4 = lane & 3;
+  }
+};
+
+// global (rows r0.., cols c0.. of an M x M matrix) -> shared 64x64 tile; out-of-range entries are 0 (1 on the diagonal
+// when `ident`), so ragged edges behave like an identity-padded matrix
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ G, long ld, int r0, int c0, int M,
+                                          bool ident) {
+  for (int e = threadIdx.x; e < TB * TB / 2; e += CT) {
+    const int r = e >> 5, c = (e & 31) * 2;
+    const int gr = r0 + r, gc = c0 + c;
+    double v0 = 0.0, v1 = 0.0;
+    if (gr < M) {
+      if (gc + 1 < M) {
+        const double2 t = *reinterpret_cast<const double2*>(G + (long)gr * ld + gc);
+        v0 = t.x;
+        v1 = t.y;
+      } else if (gc < M) {
+        v0 = G[(long)gr * ld + gc];
+      }
+    }
+    if (ident) {
+      if (gr >= M && gr == gc) v0 = 1.0;
+      if (gr >= M && gr == gc + 1) v1 = 1.0;
+    }
+    s[r * TLD + c] = v0;
+    s[r * TLD + c + 1] = v1;
+  }
+}
+
+__device__ __forceinline__ void store_tile(const double* s, double* __restrict__ G, long ld, int r0, int c0, int M) {
+  for (int e = threadIdx.x; e < TB * TB; e += CT) {
+    const int r = e >> 6, c = e & 63;
+    if (r0 + r < M && c0 + c < M) G[(long)(r0 + r) * ld + c0 + c] = s[r * TLD + c];
+  }
+}
+
+// acc += op(A) op(B) for 64x64x64 tiles in shared memory.  AT: A stored [k][m]; BT: B stored [n][k].
+template <bool AT, bool BT>
+__device__ __forceinline__ void mma_64(double (&acc)[2][4][2], const double* sA, const double* sB, const WarpPos& p) {
+#pragma unroll 4
+  for (int kk = 0; kk < TB; kk += 4) {
+    double a[2], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int m = p.wm0 + mt * 8 + p.g;
+      a[mt] = AT ? sA[(kk + p.t4) * TLD + m] : sA[m * TLD + kk + p.t4];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int n = p.wn0 + nt * 8 + p.g;
+      b[nt] = BT ? sB[n * TLD + kk + p.t4] : sB[(kk + p.t4) * TLD + n];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+
+__device__ __forceinline__ void acc_zero(double (&acc)[2][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
+__device__ __forceinline__ void acc_to_smem(const double (&acc)[2][4][2], double* s, const WarpPos& p, double scale) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = p.wm0 + mt * 8 + p.g, c = p.wn0 + nt * 8 + 2 * p.t4;
+      s[r * TLD + c] = scale * acc[mt][nt][0];
+      s[r * TLD + c + 1] = scale * acc[mt][nt][1];
+    }
+}
+
+// out = base(global tile) + scale * acc, written back to global (guarded)
+__device__ __forceinline__ void acc_axpy_global(const double (&acc)[2][4][2], double* __restrict__ G, long ld, int r0,
+                                                int c0, int M, const WarpPos& p, double scale, bool add_base) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = r0 + p.wm0 + mt * 8 + p.g, c = c0 + p.wn0 + nt * 8 + 2 * p.t4;
+      if (r < M) {
+        double* q = G + (long)r * ld + c;
+        if (c < M) q[0] = (add_base ? q[0] : 0.0) + scale * acc[mt][nt][0];
+        if (c + 1 < M) q[1] = (add_base ? q[1] : 0.0) + scale * acc[mt][nt][1];
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 64 x 64 diagonal block: factor (lower) in place in sL, inverse of the factor to sX.  Executed by threads 0..63 of the
+// CTA (two warps, named barrier 1); the other warps wait at the caller's __syncthreads.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }
+
+__device__ void factor_invert_64(double* sL, double* sX, double* sCol /* 2 x 64 */, double* sInv /* 64 */,
+                                 int global_offset, int* __restrict__ info) {
+  const int i = threadIdx.x;  // row owned (0..63)
+  double a[TB];
+#pragma unroll
+  for (int c = 0; c < TB; ++c) a[c] = sL[i * TLD + c];
+#pragma unroll
+  for (int j = 0; j < TB; ++j) {
+    if (i == j) {
+      const double dj = a[j];
+      if (!(dj > 0.0)) atomicCAS(info, 0, global_offset + j + 1);
+      const double inv = rsqrt(dj);
+      a[j] = dj * inv;
+      sInv[j] = inv;
+    }
+    bar64();
+    if (i > j) {
+      a[j] *= sInv[j];
+      sCol[(j & 1) * TB + i] = a[j];
+    }
+    bar64();
+    if (i > j) {
+      const double lij = a[j];
+      const double* col = sCol + (j & 1) * TB;
+#pragma unroll
+      for (int k = j + 1; k < TB; ++k)
+        if (k <= i) a[k] = fma(-lij, col[k], a[k]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < TB; ++c) sL[i * TLD + c] = (c <= i) ? a[c] : 0.0;
+  bar64();
+  // inverse: thread c owns column c of X = L^-1:  x_i = (delta_ic - sum_{k=c}^{i-1} l_ik x_k) / l_ii
+  const int c = threadIdx.x;
+  double x[TB];
+#pragma unroll
+  for (int r = 0; r < TB; ++r) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) {
+      if (k >= c) {
+        if (k & 1) s1 = fma(sL[r * TLD + k], x[k], s1);
+        else s0 = fma(sL[r * TLD + k], x[k], s0);
+      }
+    }
+    x[r] = (r >= c) ? (((r == c) ? 1.0 : 0.0) - (s0 + s1)) * sInv[r] : 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < TB; ++r) sX[r * TLD + c] = x[r];
+}
+
+// first diagonal block
+__global__ void __launch_bounds__(CT) potrf_first_kernel(int M, const double* __restrict__ A, long lda,
+                                                         double* __restrict__ L, long ldl, double* __restrict__ P,
+                                                         long ldp, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double *sL = sm, *sX = sm + TILE_SMEM, *sCol = sm + 2 * TILE_SMEM, *sInv = sCol + 2 * TB;
+  load_tile(sL, A, lda, 0, 0, M, true);
+  __syncthreads();
+  if (threadIdx.x < TB) factor_invert_64(sL, sX, sCol, sInv, 0, info);
+  __syncthreads();
+  store_tile(sL, L, ldl, 0, 0, M);
+  store_tile(sX, P, ldp, 0, 0, M);
+}
+
+// panel step j: for every trailing tile (i,k), j < k <= i:  A_ik -= (A_ij P_jj^T)(A_kj P_jj^T)^T; tiles with k == j+1
+// also publish L_ij; tile (j+1,j+1) additionally factors + inverts the updated block.
+__global__ void __launch_bounds__(CT) potrf_step_kernel(int M, int nblk, int j, double* __restrict__ A, long lda,
+                                                        double* __restrict__ L, long ldl, double* __restrict__ P,
+                                                        long ldp, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double *bufA = sm, *bufB = sm + TILE_SMEM, *bufP = sm + 2 * TILE_SMEM, *sCol = sm + 3 * TILE_SMEM,
+         *sInv = sCol + 2 * TB;
+  // tile index -> (a, b), 0 <= b <= a
+  int t = blockIdx.x, a = 0;
+  while ((a + 1) * (a + 2) / 2 <= t) ++a;
+  const int b = t - a * (a + 1) / 2;
+  const int i = j + 1 + a, k = j + 1 + b;
+  const WarpPos p;
+  load_tile(bufP, P, ldp, j * TB, j * TB, M, false);
+  load_tile(bufA, A, lda, i * TB, j * TB, M, false);
+  if (k != i) load_tile(bufB, A, lda, k * TB, j * TB, M, false);
+  __syncthreads();
+  double accI[2][4][2], accK[2][4][2];
+  acc_zero(accI);
+  mma_64<false, true>(accI, bufA, bufP, p);  // L_ij = A_ij P_jj^T
+  if (k != i) {
+    acc_zero(accK);
+    mma_64<false, true>(accK, bufB, bufP, p);
   }
   __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      const double dj = s[j][j];
-      if (!(dj > 0.0)) atomicCAS(info, 0, global_offset + j + 1);
-      s[j][j] = sqrt(dj);
-    }
+  acc_to_smem(accI, bufA, p, 1.0);
+  if (k != i) acc_to_smem(accK, bufB, p, 1.0);
+  __syncthreads();
+  if (b == 0) store_tile(bufA, L, ldl, i * TB, j * TB, M);
+  double acc[2][4][2];
+  acc_zero(acc);
+  mma_64<false, true>(acc, bufA, (k != i) ? bufB : bufA, p);  // L_ij L_kj^T
+  if (a == 0) {
+    // diagonal tile of the next panel: update in shared memory, then factor + invert
+    load_tile(bufP, A, lda, i * TB, i * TB, M, true);  // bufP is free (all reads of P_jj happened before the barrier)
     __syncthreads();
-    const double inv = 1.0 / s[j][j];
-    for (int i = j + 1 + tid; i < nb; i += 256) s[i][j] *= inv;
-    __syncthreads();
-    // trailing update of the lower triangle: s[i][k] -= s[i][j] * s[k][j],  j < k <= i < nb
-    const int rem = nb - j - 1;
-    for (int t = tid; t < rem * rem; t += 256) {
-      const int i = j + 1 + t / rem, k = j + 1 + t % rem;
-      if (k <= i) s[i][k] = fma(-s[i][j], s[k][j], s[i][k]);
-    }
-    __syncthreads();
-  }
-  // inverse by rows: X[i][c] = (delta_ic - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]; thread c owns column c
-  for (int i = 0; i < nb; ++i) {
-    if (tid <= i) {
-      const int c = tid;
-      double a0 = 0.0, a1 = 0.0;
-      int k = c;
-      for (; k + 1 < i; k += 2) {
-        a0 = fma(s[i][k], x[k][c], a0);
-        a1 = fma(s[i][k + 1], x[k + 1][c], a1);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = p.wm0 + mt * 8 + p.g, c = p.wn0 + nt * 8 + 2 * p.t4;
+        bufP[r * TLD + c] -= acc[mt][nt][0];
+        bufP[r * TLD + c + 1] -= acc[mt][nt][1];
       }
-      if (k < i) a0 = fma(s[i][k], x[k][c], a0);
-      x[i][c] = (((i == c) ? 1.0 : 0.0) - (a0 + a1)) / s[i][i];
+    __syncthreads();
+    if (threadIdx.x < TB) factor_invert_64(bufP, bufB, sCol, sInv, i * TB, info);
+    __syncthreads();
+    store_tile(bufP, L, ldl, i * TB, i * TB, M);
+    store_tile(bufB, P, ldp, i * TB, i * TB, M);
+  } else {
+    acc_axpy_global(acc, A, lda, i * TB, k * TB, M, p, -1.0, true);
+  }
+}
+
+// recursive-doubling level, phase 0: T = L21 P11 for every block pair of the level (blockIdx.z = pair);
+// phase 1: P21 = -P22 T.  Blocks are b x b (b a multiple of 64), tiles 64 x 64.
+__global__ void __launch_bounds__(CT) trinv_level_kernel(int M, int b, int phase, const double* __restrict__ Lm,
+                                                         long ldl, double* __restrict__ P, long ldp,
+                                                         double* __restrict__ work) {
+  extern __shared__ double sm[];
+  double *bufA = sm, *bufB = sm + TILE_SMEM;
+  const int s = blockIdx.z * 2 * b;     // pair start
+  const int r1 = s + b;                 // first row of block 2
+  if (r1 >= M) return;
+  const int b2 = min(b, M - r1);
+  const int tr = blockIdx.y, tc = blockIdx.x;  // tile row within block 2, tile col within block 1
+  if (tr * TB >= b2) return;
+  const WarpPos p;
+  double* T = work + (long)blockIdx.z * b * b;  // (b2 x b), ld = b
+  double acc[2][4][2];
+  acc_zero(acc);
+  const int nkb = b / TB;
+  // phase 0: k runs over block-1 tiles with k >= tc (P11 lower);  phase 1: over block-2 tiles with k <= tr (P22 lower)
+  const int k_lo = (phase == 0) ? tc : 0;
+  const int k_hi = (phase == 0) ? nkb : min(tr + 1, (b2 + TB - 1) / TB);
+  for (int kb = k_lo; kb < k_hi; ++kb) {
+    __syncthreads();
+    if (phase == 0) {
+      load_tile(bufA, Lm, ldl, r1 + tr * TB, s + kb * TB, M, false);
+      load_tile(bufB, P, ldp, s + kb * TB, s + tc * TB, M, false);
+    } else {
+      load_tile(bufA, P, ldp, r1 + tr * TB, r1 + kb * TB, M, false);
+      // T tile (rows kb, cols tc) of the b2 x b workspace; reuse load_tile with a virtual M bound
+      for (int e = threadIdx.x; e < TB * TB; e += CT) {
+        const int r = e >> 6, c = e & 63;
+        const int rr = kb * TB + r;
+        bufB[r * TLD + c] = (rr < b2) ? T[(long)rr * b + tc * TB + c] : 0.0;
+      }
     }
     __syncthreads();
+    mma_64<false, false>(acc, bufA, bufB, p);
   }
-  for (int t = tid; t < nb * nb; t += 256) {
-    const int r = t / nb, c = t % nb;
-    A[(long)r * lda + c] = (c <= r) ? s[r][c] : 0.0;
-    Pd[(long)r * ldp + c] = (c <= r) ? x[r][c] : 0.0;
+  if (phase == 0) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int r = tr * TB + p.wm0 + mt * 8 + p.g, c = tc * TB + p.wn0 + nt * 8 + 2 * p.t4;
+        if (r < b2) {
+          T[(long)r * b + c] = acc[mt][nt][0];
+          T[(long)r * b + c + 1] = acc[mt][nt][1];
+        }
+      }
+  } else {
+    acc_axpy_global(acc, P, ldp, r1 + tr * TB, s + tc * TB, M, p, -1.0, false);
   }
 }
 
-// zero the strict upper triangle outside the diagonal blocks (diag blocks are written clean by potrf_diag_kernel)
-__global__ void zero_upper_blocks_kernel(int M, double* A, long lda, double* P, long ldp) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y * blockDim.y + threadIdx.y;
-  if (r >= M || c >= M) return;
-  if (c / NB > r / NB) {
-    if (A) A[(long)r * lda + c] = 0.0;
-    if (P) P[(long)r * ldp + c] = 0.0;
-  }
+__global__ void copy_matrix_kernel(int M, const double* __restrict__ S, long lds, double* __restrict__ D, long ldd) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * M) return;
+  const int r = (int)(idx / M), c = (int)(idx % M);
+  D[(long)r * ldd + c] = S[(long)r * lds + c];
 }
 
-constexpr int DIAG_SMEM = 2 * NB * LDB * (int)sizeof(double);
+__global__ void zero_matrix_kernel(int M, double* __restrict__ D, long ldd) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)M * M) return;
+  D[(long)(idx / M) * ldd + (idx % M)] = 0.0;
+}
+
+constexpr int FIRST_SMEM = (2 * TILE_SMEM + 3 * TB) * (int)sizeof(double);
+constexpr int STEP_SMEM = (3 * TILE_SMEM + 3 * TB) * (int)sizeof(double);
+constexpr int LEVEL_SMEM = 2 * TILE_SMEM * (int)sizeof(double);
+
+static long work_doubles(int M) {
+  const long Mp = ((long)M + TB - 1) / TB * TB;
+  return Mp * Mp + Mp * Mp / 2 + (long)TB * Mp;
+}
 
 int potrf_inv_impl(int M, double* A, long lda, double* P, long ldp, double* work, int* info, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    NPGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+    NPGP_CUDA(cudaFuncSetAttribute(potrf_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
+    NPGP_CUDA(cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
+    NPGP_CUDA(cudaFuncSetAttribute(trinv_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
     attr_set = true;
   }
+  const int nblk = (M + TB - 1) / TB;
+  double* L = work;  // M x M, ld = M
+  const long ldl = M + (M & 1);
+  double* T = work + (long)M * ldl;
+  const unsigned nbk = (unsigned)(((long)M * M + 255) / 256);
   NPGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
-  for (int j0 = 0; j0 < M; j0 += NB) {
-    const int nb = (M - j0 < NB) ? (M - j0) : NB;
-    double* A11 = A + (long)j0 * lda + j0;
-    double* P11 = P + (long)j0 * ldp + j0;
-    potrf_diag_kernel<<<1, 256, DIAG_SMEM, st>>>(nb, A11, lda, P11, ldp, j0, info);
-    NPGP_LAUNCH_CHECK();
-    const int m2 = M - j0 - nb;
-    if (m2 <= 0) break;
-    double* A21 = A + (long)(j0 + nb) * lda + j0;
-    double* A22 = A + (long)(j0 + nb) * lda + (j0 + nb);
-    // L21 = A21 * P11^T   (in place: each CTA reads and writes only its own 128 rows, N = nb <= 128 is one tile)
-    int rc = dgemm_impl(0, 1, m2, nb, nb, 1.0, A21, lda, P11, ldp, 0.0, A21, lda, 0, 0, 0, st);
-    if (rc) return rc;
-    // A22 -= L21 L21^T  (lower tiles only)
-    rc = dgemm_impl(0, 1, m2, m2, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, 0, 0, 1, st);
-    if (rc) return rc;
-  }
-  {
-    dim3 blk(32, 8), grd(ceil_div(M, 32), ceil_div(M, 8));
-    zero_upper_blocks_kernel<<<grd, blk, 0, st>>>(M, A, lda, P, ldp);
+  NPGP_CUDA(cudaMemsetAsync(L, 0, sizeof(double) * M * ldl, st));
+  zero_matrix_kernel<<<nbk, 256, 0, st>>>(M, P, ldp);
+  NPGP_LAUNCH_CHECK();
+  potrf_first_kernel<<<1, CT, FIRST_SMEM, st>>>(M, A, lda, L, ldl, P, ldp, info);
+  NPGP_LAUNCH_CHECK();
+  for (int j = 0; j + 1 < nblk; ++j) {
+    const int r = nblk - 1 - j;
+    potrf_step_kernel<<<r * (r + 1) / 2, CT, STEP_SMEM, st>>>(M, nblk, j, A, lda, L, ldl, P, ldp, info);
     NPGP_LAUNCH_CHECK();
   }
-  // assemble P = L^-1 by recursive doubling; `work` holds T = L21 P11 (at most (M/2)^2 doubles, ld = b)
-  for (int b = NB; b < M; b *= 2) {
-    for (int s = 0; s + b < M; s += 2 * b) {
-      const int b2 = (M - s - b < b) ? (M - s - b) : b;
-      const double* L21 = A + (long)(s + b) * lda + s;
-      const double* P11 = P + (long)s * ldp + s;
-      const double* P22 = P + (long)(s + b) * ldp + (s + b);
-      double* P21 = P + (long)(s + b) * ldp + s;
-      int rc = dgemm_impl(0, 0, b2, b, b, 1.0, L21, lda, P11, ldp, 0.0, work, b, 0, 1, 0, st);
-      if (rc) return rc;
-      rc = dgemm_impl(0, 0, b2, b, b2, -1.0, P22, ldp, work, b, 0.0, P21, ldp, 1, 0, 0, st);
-      if (rc) return rc;
-    }
+  for (int b = TB; b < M; b *= 2) {
+    const int pairs = (M + 2 * b - 1) / (2 * b);
+    dim3 grid(b / TB, b / TB, pairs);
+    trinv_level_kernel<<<grid, CT, LEVEL_SMEM, st>>>(M, b, 0, L, ldl, P, ldp, T);
+    NPGP_LAUNCH_CHECK();
+    trinv_level_kernel<<<grid, CT, LEVEL_SMEM, st>>>(M, b, 1, L, ldl, P, ldp, T);
+    NPGP_LAUNCH_CHECK();
   }
+  copy_matrix_kernel<<<nbk, 256, 0, st>>>(M, L, ldl, A, lda);
+  NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
 
@@ -138,17 +378,15 @@ int potrf_inv_impl(int M, double* A, long lda, double* P, long ldp, double* work
 
 using namespace npgp;
 
-extern "C" long npgp_potrf_workspace_bytes(int M) {
-  long h = (M + 1) / 2 + NB;
-  return h * h * (long)sizeof(double);
-}
+extern "C" long npgp_potrf_workspace_bytes(int M) { return work_doubles(M) * (long)sizeof(double); }
 
 extern "C" int npgp_potrf_inv_lower(int M, double* A, long lda, double* P, long ldp, void* work, long work_bytes,
                                     int* info, cudaStream_t stream) {
   if (M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
   if (!A || !P || !info || !work) return NPGP_EINVAL;
-  if ((lda & 1) || (ldp & 1)) return NPGP_EUNSUPPORTED;
+  if ((lda & 1) || (ldp & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(P) & 15))
+    return NPGP_EUNSUPPORTED;
   if (work_bytes < npgp_potrf_workspace_bytes(M)) return NPGP_EWORKSPACE;
   return potrf_inv_impl(M, A, lda, P, ldp, static_cast<double*>(work), info, stream);
 }

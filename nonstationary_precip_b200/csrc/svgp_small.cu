@@ -94,9 +94,43 @@ __global__ void adam_kernel(long n, double* __restrict__ p, const double* __rest
   p[i] -= lr * (mi / bc1) / (sqrt(vi / bc2) + eps);
 }
 
+// Adam with the step counter on the device (so that a captured CUDA graph replays with the right bias correction):
+// step_dev[0] holds the number of steps taken so far; bump_step_kernel increments it after the update.
+__global__ void adam_dev_kernel(long n, double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
+                                double* __restrict__ v, const double* __restrict__ mask, double lr, double b1,
+                                double b2, double eps, const double* __restrict__ step_dev, double gscale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask && mask[i] == 0.0) return;
+  const double t = step_dev[0] + 1.0;
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  const double gi = gscale * g[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / bc1) / (sqrt(vi / bc2) + eps);
+}
+
+__global__ void bump_step_kernel(double* step_dev) { step_dev[0] += 1.0; }
+
 }  // namespace npgp
 
 using namespace npgp;
+
+extern "C" int npgp_adam_step_dev(long n, double* p, const double* g, double* m, double* v, const double* mask,
+                                  double lr, double beta1, double beta2, double eps, double* step_dev, double gscale,
+                                  cudaStream_t stream) {
+  if (n < 0 || !step_dev) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!p || !g || !m || !v) return NPGP_EINVAL;
+  adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, p, g, m, v, mask, lr, beta1, beta2, eps, step_dev,
+                                                                   gscale);
+  NPGP_LAUNCH_CHECK();
+  bump_step_kernel<<<1, 1, 0, stream>>>(step_dev);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
 
 extern "C" int npgp_colwsum(int n, int M, const double* K, long ldk, const double* w, double* out,
                             cudaStream_t stream) {

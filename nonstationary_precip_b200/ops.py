@@ -229,6 +229,14 @@ def adam_step_(p, g, m, v, step, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, gsca
     return p
 
 
+def adam_step_dev_(p, g, m, v, step_dev, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, mask=None):
+    """Adam with the step counter on the device (graph-capturable)."""
+    check(lib().npgp_adam_step_dev(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), ptr(mask), float(lr), float(beta1),
+                                   float(beta2), float(eps), ptr(step_dev), float(gscale), stream()),
+          "npgp_adam_step_dev")
+    return p
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # autograd Functions (analytic backward kernels)
 # ----------------------------------------------------------------------------------------------------------------------

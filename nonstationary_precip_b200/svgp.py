@@ -17,6 +17,7 @@ Gradient chain used below (E = S - I, S = Ls Ls^T, P = L^-1, L = chol(Kzz + jitt
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Optional
 
@@ -111,6 +112,10 @@ class SVGPGibbs:
             self._mask_views["Z"].zero_()
         self.eye = torch.eye(M, **f64)
         self.step_count = 0
+        self.step_dev = torch.zeros(1, **f64)  # Adam step counter on the device
+        self._side = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
+        self.overlap = True
+        self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
 
     def _sec(self, name):
@@ -155,13 +160,32 @@ class SVGPGibbs:
         return o.dgemm(P, T, transA=True, tri_a=2)[:, :k].contiguous()
 
     # ------------------------------------------------------------------------------------------------------------------
-    def _field_forward(self, x):
-        """Latent field at Z and interpolated to the rows x.  Returns (fz, fx, cache)."""
+    def _field_z(self):
+        """Latent field at the inducing points: ell_z (D,M) or packed Sigma_z (M,P)."""
+        if self.variant == "diag":
+            return torch.exp(self.p["log_ell_z"])
+        return self.o.sigma_from_h_fwd(self.p["H"], self.p["D"])
+
+    def _fork(self):
+        """Run the enclosed launches on the side stream, ordered after everything enqueued so far."""
+        if self._side is None or not self.overlap:
+            return contextlib.nullcontext()
+        self._side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side)
+
+    def _join(self):
+        if self._side is not None and self.overlap:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    def _field_forward(self, x, fz=None):
+        """Latent field interpolated from Z to the rows x.  Returns (fz, fx, cache)."""
         o, p, M, d = self.o, self.p, self.M, self.d
         Z = p["Z"]
         c = {}
+        if fz is None:
+            fz = self._field_z()
         if self.variant == "diag":
-            ell_z = torch.exp(p["log_ell_z"])
+            ell_z = fz
             alphas, Ps, Linvdiag = [], [], []
             for b in range(d):
                 lamb = self._bcast_ell(self.prior_lam[b], M)
@@ -176,7 +200,7 @@ class SVGPGibbs:
                                      apply_exp=True).squeeze(-1)
             c.update(alpha=alpha, Ps=Ps, Ldiag=Linvdiag, ell_z=ell_z, ell_x=ell_x)
             return ell_z, ell_x, c
-        Sz = o.sigma_from_h_fwd(p["H"], p["D"])
+        Sz = fz
         lamr = self._bcast_ell(self.row_lam[0], M)
         Kr = o.gibbs_diag_fwd(Z, lamr, Z, lamr, self.row_os)
         Kr.diagonal().add_(1e-5)
@@ -212,10 +236,13 @@ class SVGPGibbs:
         noise = 1e-4 + _softplus(p["raw_noise"])
         self.grad.zero_()
 
+        fz = self._field_z()
+        with self._fork():  # Kzz -> Cholesky -> u, C on the side stream, overlapped with the field interpolation
+            with self._sec("zz_fwd(potrf+M^3)"):
+                zz = self._zz_forward(fz, s)
         with self._sec("field_fwd"):
-            fz, fx, fc = self._field_forward(xb)
-        with self._sec("zz_fwd(potrf+M^3)"):
-            zz = self._zz_forward(fz, s)
+            fz, fx, fc = self._field_forward(xb, fz)
+        self._join()
         P, u, E, C, Ls = zz["P"], zz["u"], zz["E"], zz["C"], zz["Ls"]
 
         # ---- data pass: K(X_B, Z) (+ mean), variance quadratic form, expected log-lik
@@ -239,31 +266,32 @@ class SVGPGibbs:
         elbo_local = ell + rep * (-kl + lp) / self.N
 
         # ---- backward of the data term through K(X_B, Z)
+        gv2 = 2.0 * gv
+        with self._fork():  # side stream: reductions over rows, then the O(M^3) backward chain u, C -> m, Ls, Kzz
+            with self._sec("colwsum"):
+                du = o.colwsum(K, w=gmu)
+            with self._sec("wsyrk"):
+                dC = o.wsyrk(K, w=gv)
+            with self._sec("m3_bwd+kzz_bwd"):
+                dm = o.gemv_n(P, du)
+                dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
+                X = o.dgemm(E, dE, alpha=2.0)
+                X.addr_(m, dm)
+                o.phi_mask_(X, -1.0)
+                dK = o.dgemm(o.dgemm(P, X, transA=True, tri_a=2, tri_b=1), P, tri_b=1)
+                dKzz = 0.5 * (dK + dK.T)
+                dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
+                g["m"].copy_(-(dm - rep * m / self.N))
+                g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
+                dfz1, dfz2, dZ1, dZ2, ds2 = self._kernel_bwd(Z, fz, Z, fz, s, G=dKzz, need_dx1=self.learn_z,
+                                                             need_dx2=self.learn_z, need_dscale=True)
         with self._sec("kxz_bwd"):
-            dfx, dfz, _, dZ, ds = self._kernel_bwd(xb, fx, Z, fz, s, G=T, rowscale=2.0 * gv, rowvec=gmu, colvec=u,
+            dfx, dfz, _, dZ, ds = self._kernel_bwd(xb, fx, Z, fz, s, G=T, rowscale=gv2, rowvec=gmu, colvec=u,
                                                    need_dx2=self.learn_z, need_dscale=True)
-        with self._sec("colwsum"):
-            du = o.colwsum(K, w=gmu)
-        with self._sec("wsyrk"):
-            dC = o.wsyrk(K, w=gv)
         ds = ds + gv.sum()  # v = s + ...
-        sec_m3 = self._sec("m3_bwd+kzz_bwd+field_bwd")
+        self._join()
+        sec_m3 = self._sec("field_bwd+assemble")
         sec_m3.__enter__()
-
-        # ---- O(M^3) backward: u, C -> m, Ls, Kzz
-        dm = o.gemv_n(P, du)
-        dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
-        X = o.dgemm(E, dE, alpha=2.0)
-        X.addr_(m, dm)
-        o.phi_mask_(X, -1.0)
-        dK = o.dgemm(o.dgemm(P, X, transA=True, tri_a=2, tri_b=1), P, tri_b=1)
-        dKzz = 0.5 * (dK + dK.T)
-        dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
-        g["m"].copy_(-(dm - rep * m / self.N))
-        g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
-
-        dfz1, dfz2, dZ1, dZ2, ds2 = self._kernel_bwd(Z, fz, Z, fz, s, G=dKzz, need_dx1=self.learn_z,
-                                                     need_dx2=self.learn_z, need_dscale=True)
         dfz = dfz + dfz1 + dfz2
         ds = ds + ds2
         gZ = torch.zeros_like(Z)
@@ -326,8 +354,13 @@ class SVGPGibbs:
     # ------------------------------------------------------------------------------------------------------------------
     def adam_step(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
         self.step_count += 1
-        self.o.adam_step_(self.theta, self.grad[:self.theta.numel()], self.adam_m, self.adam_v, self.step_count, lr,
-                          beta1, beta2, eps, 1.0, self.mask)
+        g = self.grad[:self.theta.numel()]
+        if hasattr(self.o, "adam_step_dev_"):  # step counter on the device: identical eagerly and under graph replay
+            self.o.adam_step_dev_(self.theta, g, self.adam_m, self.adam_v, self.step_dev, lr, beta1, beta2, eps, 1.0,
+                                  self.mask)
+        else:
+            self.o.adam_step_(self.theta, g, self.adam_m, self.adam_v, self.step_count, lr, beta1, beta2, eps, 1.0,
+                              self.mask)
 
     def train_step(self, xb, yb, lr=0.01, world_size=1, B_global=None, all_reduce=None):
         """loss_and_grad -> (all-reduce of the flat gradient) -> Adam.  Returns the (global) loss as a device scalar."""
@@ -335,6 +368,43 @@ class SVGPGibbs:
         if all_reduce is not None:
             all_reduce(self.grad)
         self.adam_step(lr)
+        return self.grad[-2]
+
+    # ---- CUDA-graph execution: the ~250 launches of a step are captured once and replayed ---------------------------
+    def capture(self, B_local: int, world_size: int = 1, B_global: Optional[int] = None, lr: float = 0.01):
+        """Capture loss_and_grad (and, single rank, the Adam update) for minibatches of B_local rows.  With several
+        ranks the NCCL all-reduce and the Adam kernel run between / after the replayed graph."""
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self._gx, self._gy = torch.zeros(B_local, self.d, **f64), torch.zeros(B_local, **f64)
+        self._g_world, self._g_lr = world_size, lr
+        snap = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.step_dev)]
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the default stream (allocator pools, lazy attribute calls)
+            for _ in range(2):
+                self.loss_and_grad(self._gx, self._gy, world_size, B_global)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.loss_and_grad(self._gx, self._gy, world_size, B_global)
+            if world_size == 1:
+                self.adam_step(lr)
+        for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
+            t.copy_(s)
+        self.step_count = int(self.step_dev.item())
+
+    def train_step_graph(self, xb, yb, all_reduce=None):
+        """Replay of the captured step on a new minibatch (xb, yb may live in pinned host memory)."""
+        self._gx.copy_(xb, non_blocking=True)
+        self._gy.copy_(yb, non_blocking=True)
+        self._graph.replay()
+        if self._g_world > 1:
+            if all_reduce is not None:
+                all_reduce(self.grad)
+            self.adam_step(self._g_lr)
+        else:
+            self.step_count += 1
         return self.grad[-2]
 
     @torch.no_grad()

@@ -95,7 +95,7 @@ def test_full_size_properties(variant):
     for r in range(2):
         model.loss_and_grad(x[r::2].contiguous(), y[r::2].contiguous(), world_size=2)
         tot += model.grad
-    assert rel(tot, g_full) < 1e-9
+    assert rel(tot, g_full) < 1e-7  # summation order x conditioning of the C = P^T (S-I) P form
     # (2) K(Z,Z) has a unit diagonal (outputscale 1) and is symmetric
     fz, _, _ = model._field_forward(x[:64].contiguous())
     Kzz = model._kernel_fwd(model.p["Z"], fz, model.p["Z"], fz, None)
