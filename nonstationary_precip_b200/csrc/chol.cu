@@ -13,9 +13,9 @@
 //     needs (L_ij = A_ij P_jj^T, L_kj = A_kj P_jj^T: redundant 64^3 DMMA work instead of a separate TRSM launch and a
 //     grid-wide dependency), applies A_ik -= L_ij L_kj^T, and the CTA of tile (j+1,j+1) goes on to factor AND invert the
 //     freshly updated diagonal block, so the next step can start as soon as this kernel retires (look-ahead of 1).
-//   * The 64x64 diagonal block is factored by 64 threads that hold one matrix row each in registers (fully unrolled
-//     right-looking elimination, one rsqrt per pivot, column broadcast through shared memory, two 64-thread named
-//     barriers per column) and inverted column-per-thread by forward substitution.
+//   * The 64x64 diagonal block is factored in shared memory by a blocked (8-wide) right-looking elimination whose loop
+//     bodies are small and re-executed (a fully unrolled 64-column version measured 110 us: instruction-fetch bound),
+//     one rsqrt per pivot, and inverted by recursive doubling 8 -> 16 -> 32 -> 64 (see factor_invert_64).
 //   * L^-1 is assembled by recursive doubling, inv([[L11,0],[L21,L22]]) = [[P11,0],[-P22 L21 P11, P22]]: two batched
 //     kernels per level (all block pairs of a level in one launch), skipping the structurally zero blocks.
 // All tile products run on the FP64 tensor pipe (DMMA.8x8x4).
@@ -136,60 +136,110 @@ __device__ __forceinline__ void acc_axpy_global(const double (&acc)[2][4][2], do
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 64 x 64 diagonal block: factor (lower) in place in sL, inverse of the factor to sX.  Executed by threads 0..63 of the
-// CTA (two warps, named barrier 1); the other warps wait at the caller's __syncthreads.
+// 64 x 64 diagonal block (symmetric input in s, lower part used): Cholesky factor in place (upper zeroed) and the
+// inverse of the factor in x.  All 256 threads.  Blocked by 8 so that every loop body is small and re-executed (a fully
+// unrolled 64-column elimination is instruction-fetch bound): the 8x8 pivot block is factored and inverted serially in
+// the registers of one thread (the critical path is the 64 dependent rsqrt's anyway), the panel below it is one row
+// per thread, the trailing update one element per thread.  The inverse is then assembled by recursive doubling
+// (8 -> 16 -> 32 -> 64) with element-per-thread products.  tmp: >= 32*32 doubles.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }
-
-__device__ void factor_invert_64(double* sL, double* sX, double* sCol /* 2 x 64 */, double* sInv /* 64 */,
-                                 int global_offset, int* __restrict__ info) {
-  const int i = threadIdx.x;  // row owned (0..63)
-  double a[TB];
+__device__ __forceinline__ void chol8_serial(double* s, double* x, int c0, int global_offset, int* __restrict__ info) {
+  double a[8][8], xi[8][8], inv[8];
 #pragma unroll
-  for (int c = 0; c < TB; ++c) a[c] = sL[i * TLD + c];
+  for (int r = 0; r < 8; ++r)
 #pragma unroll
-  for (int j = 0; j < TB; ++j) {
-    if (i == j) {
-      const double dj = a[j];
-      if (!(dj > 0.0)) atomicCAS(info, 0, global_offset + j + 1);
-      const double inv = rsqrt(dj);
-      a[j] = dj * inv;
-      sInv[j] = inv;
-    }
-    bar64();
-    if (i > j) {
-      a[j] *= sInv[j];
-      sCol[(j & 1) * TB + i] = a[j];
-    }
-    bar64();
-    if (i > j) {
-      const double lij = a[j];
-      const double* col = sCol + (j & 1) * TB;
+    for (int c = 0; c <= r; ++c) a[r][c] = s[(c0 + r) * TLD + c0 + c];
 #pragma unroll
-      for (int k = j + 1; k < TB; ++k)
-        if (k <= i) a[k] = fma(-lij, col[k], a[k]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    const double dj = a[j][j];
+    if (!(dj > 0.0)) atomicCAS(info, 0, global_offset + c0 + j + 1);
+    inv[j] = rsqrt(dj);
+    a[j][j] = dj * inv[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) a[i][j] *= inv[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
   }
 #pragma unroll
-  for (int c = 0; c < TB; ++c) sL[i * TLD + c] = (c <= i) ? a[c] : 0.0;
-  bar64();
-  // inverse: thread c owns column c of X = L^-1:  x_i = (delta_ic - sum_{k=c}^{i-1} l_ik x_k) / l_ii
-  const int c = threadIdx.x;
-  double x[TB];
+  for (int c = 0; c < 8; ++c)
 #pragma unroll
-  for (int r = 0; r < TB; ++r) {
-    double s0 = 0.0, s1 = 0.0;
+    for (int r = c; r < 8; ++r) {
+      double acc = (r == c) ? 1.0 : 0.0;
 #pragma unroll
-    for (int k = 0; k < r; ++k) {
-      if (k >= c) {
-        if (k & 1) s1 = fma(sL[r * TLD + k], x[k], s1);
-        else s0 = fma(sL[r * TLD + k], x[k], s0);
+      for (int k = c; k < r; ++k) acc = fma(-a[r][k], xi[k][c], acc);
+      xi[r][c] = acc * inv[r];
+    }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      s[(c0 + r) * TLD + c0 + c] = (c <= r) ? a[r][c] : 0.0;
+      x[(c0 + r) * TLD + c0 + c] = (c <= r) ? xi[r][c] : 0.0;
+    }
+}
+
+__device__ void factor_invert_64(double* s, double* x, double* tmp, int global_offset, int* __restrict__ info) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < TB * TB; e += CT) x[(e >> 6) * TLD + (e & 63)] = 0.0;
+  __syncthreads();
+  for (int c0 = 0; c0 < TB; c0 += 8) {
+    if (tid == 0) chol8_serial(s, x, c0, global_offset, info);
+    __syncthreads();
+    const int r1 = c0 + 8, n = TB - r1;
+    // panel: row r of L[:, c0:c0+8] = A[r, c0:c0+8] * X8^T  (X8 lower: X8[c][k], k <= c)
+    if (tid < n) {
+      const int r = r1 + tid;
+      double a[8], l[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = s[r * TLD + c0 + k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= c; ++k) acc = fma(a[k], x[(c0 + c) * TLD + c0 + k], acc);
+        l[c] = acc;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        s[r * TLD + c0 + c] = l[c];
+        s[(c0 + c) * TLD + r] = 0.0;  // zero the mirrored (upper) entries
       }
     }
-    x[r] = (r >= c) ? (((r == c) ? 1.0 : 0.0) - (s0 + s1)) * sInv[r] : 0.0;
-  }
+    __syncthreads();
+    // trailing update of the lower triangle: s[i][k] -= sum_c s[i][c0+c] * s[k][c0+c],  r1 <= k <= i < 64
+    for (int e = tid; e < n * n; e += CT) {
+      const int i = r1 + e / n, k = r1 + e % n;
+      if (k <= i) {
+        double acc = s[i * TLD + k];
 #pragma unroll
-  for (int r = 0; r < TB; ++r) sX[r * TLD + c] = x[r];
+        for (int c = 0; c < 8; ++c) acc = fma(-s[i * TLD + c0 + c], s[k * TLD + c0 + c], acc);
+        s[i * TLD + k] = acc;
+      }
+    }
+    __syncthreads();
+  }
+  // inverse by doubling: for block pairs (size sz): T = L21 X11;  X21 = -X22 T
+  for (int sz = 8; sz < TB; sz *= 2) {
+    const int pairs = TB / (2 * sz);
+    for (int e = tid; e < pairs * sz * sz; e += CT) {
+      const int pr = e / (sz * sz), q = e % (sz * sz), r = q / sz, c = q % sz;
+      const int b0 = pr * 2 * sz;
+      double acc = 0.0;
+      for (int k = c; k < sz; ++k) acc = fma(s[(b0 + sz + r) * TLD + b0 + k], x[(b0 + k) * TLD + b0 + c], acc);
+      tmp[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < pairs * sz * sz; e += CT) {
+      const int pr = e / (sz * sz), q = e % (sz * sz), r = q / sz, c = q % sz;
+      const int b0 = pr * 2 * sz;
+      double acc = 0.0;
+      for (int k = 0; k <= r; ++k) acc = fma(x[(b0 + sz + r) * TLD + b0 + sz + k], tmp[pr * sz * sz + k * sz + c], acc);
+      x[(b0 + sz + r) * TLD + b0 + c] = -acc;
+    }
+    __syncthreads();
+  }
 }
 
 // first diagonal block
@@ -197,11 +247,10 @@ __global__ void __launch_bounds__(CT) potrf_first_kernel(int M, const double* __
                                                          double* __restrict__ L, long ldl, double* __restrict__ P,
                                                          long ldp, int* __restrict__ info) {
   extern __shared__ double sm[];
-  double *sL = sm, *sX = sm + TILE_SMEM, *sCol = sm + 2 * TILE_SMEM, *sInv = sCol + 2 * TB;
+  double *sL = sm, *sX = sm + TILE_SMEM, *tmp = sm + 2 * TILE_SMEM;
   load_tile(sL, A, lda, 0, 0, M, true);
   __syncthreads();
-  if (threadIdx.x < TB) factor_invert_64(sL, sX, sCol, sInv, 0, info);
-  __syncthreads();
+  factor_invert_64(sL, sX, tmp, 0, info);
   store_tile(sL, L, ldl, 0, 0, M);
   store_tile(sX, P, ldp, 0, 0, M);
 }
@@ -212,8 +261,7 @@ __global__ void __launch_bounds__(CT) potrf_step_kernel(int M, int nblk, int j, 
                                                         double* __restrict__ L, long ldl, double* __restrict__ P,
                                                         long ldp, int* __restrict__ info) {
   extern __shared__ double sm[];
-  double *bufA = sm, *bufB = sm + TILE_SMEM, *bufP = sm + 2 * TILE_SMEM, *sCol = sm + 3 * TILE_SMEM,
-         *sInv = sCol + 2 * TB;
+  double *bufA = sm, *bufB = sm + TILE_SMEM, *bufP = sm + 2 * TILE_SMEM;
   // tile index -> (a, b), 0 <= b <= a
   int t = blockIdx.x, a = 0;
   while ((a + 1) * (a + 2) / 2 <= t) ++a;
@@ -252,8 +300,7 @@ __global__ void __launch_bounds__(CT) potrf_step_kernel(int M, int nblk, int j, 
         bufP[r * TLD + c + 1] -= acc[mt][nt][1];
       }
     __syncthreads();
-    if (threadIdx.x < TB) factor_invert_64(bufP, bufB, sCol, sInv, i * TB, info);
-    __syncthreads();
+    factor_invert_64(bufP, bufB, bufA, i * TB, info);  // bufA (L_ij, no longer needed) serves as scratch
     store_tile(bufP, L, ldl, i * TB, i * TB, M);
     store_tile(bufB, P, ldp, i * TB, i * TB, M);
   } else {
@@ -328,8 +375,8 @@ __global__ void zero_matrix_kernel(int M, double* __restrict__ D, long ldd) {
   D[(long)(idx / M) * ldd + (idx % M)] = 0.0;
 }
 
-constexpr int FIRST_SMEM = (2 * TILE_SMEM + 3 * TB) * (int)sizeof(double);
-constexpr int STEP_SMEM = (3 * TILE_SMEM + 3 * TB) * (int)sizeof(double);
+constexpr int FIRST_SMEM = 3 * TILE_SMEM * (int)sizeof(double);
+constexpr int STEP_SMEM = 3 * TILE_SMEM * (int)sizeof(double);
 constexpr int LEVEL_SMEM = 2 * TILE_SMEM * (int)sizeof(double);
 
 static long work_doubles(int M) {

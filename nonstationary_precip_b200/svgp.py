@@ -132,6 +132,15 @@ class SVGPGibbs:
     def state_dict(self):
         return {k: v.clone() for k, v in self.p.items()}
 
+    def snapshot(self):
+        """Parameters + optimiser state (for restarting a run from the same point)."""
+        return [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.step_dev)]
+
+    def restore(self, snap):
+        for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
+            t.copy_(s)
+        self.step_count = int(self.step_dev.item())
+
     def _bcast_ell(self, lam_row, n):
         return lam_row.reshape(-1, 1).expand(self.d, n).contiguous()
 
