@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -274,6 +274,11 @@ def run_ours(args):
     e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
 
     # ---- per-kernel evidence for the roofline (CUDA events around the sections of a few extra steps)
+    model.restore(snap)
+    model.overlap = False
+    for k in range(2):  # unprofiled eager steps first: the eager allocator pool (K, T: 512 MiB each) is cold after graphs
+        lo, hi = rows(k)
+        model.train_step(X[lo:hi], Y[lo:hi], lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce)
     model.restore(snap)
     model.profile = {}
     for k in range(3):  # eager, one stream, so that the CUDA-event brackets see each section alone
