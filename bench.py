@@ -184,6 +184,10 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # libraries (NCCL's version banner) write to fd 1; keep stdout clean for the single JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -335,7 +339,10 @@ def run_ours(args):
                 "value": 1.0 / t_cpu, "unit": "steps/s", "cores": threads, "kind": "port",
                 "sample": "%d of %d minibatch rows (M=%d) fwd+autograd bwd of the oracle, time scaled x%d" % (
                     cpu_rows, B_GLOBAL, M_IND, B_GLOBAL // cpu_rows)}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
