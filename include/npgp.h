@@ -90,6 +90,8 @@ int npgp_rowquad(int n, int M, const double* K, long ldk, const double* C, long 
 int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const double* w, double* Out, long ldo,
                npgp_stream_t stream);
 int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t stream);
+/* measurement switch for the GEMM family: 0 = 128x128 tiles (1 CTA/SM), 1 = 128x64 tiles (2 CTAs/SM, default) */
+int npgp_set_gemm_config(int cfg);
 
 /* ---- (c) blocked Cholesky + inverse factor --------------------------------------------------------------------------
  * A = L L^T in place (upper zeroed), P = L^-1; *info = 0 or 1-based index of the first non-positive pivot.

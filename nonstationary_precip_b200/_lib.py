@@ -35,6 +35,7 @@ _SIGS = {
     "npgp_potrf_workspace_bytes": ([_i], _l),
     "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
+    "npgp_set_gemm_config": ([_i], _i),
     "npgp_colwsum": ([_i, _i, _p, _l, _p, _p, _p], _i),
     "npgp_gemv_n": ([_i, _i, _p, _l, _p, _p, _p], _i),
     "npgp_gauss_ell": ([_i, _p, _p, _p, _p, _d, _d, _p, _d, _p, _p, _p, _p, _p], _i),

@@ -7,20 +7,18 @@
 // These replace the cuBLAS/MAGMA calls GPyTorch issues for  A = L^-1 Kzx,  A^T (S - I) A  and  Kzx Kxz
 // (reference models/gibbs_kernels.py:222-232 via LowRankRootLazyTensor; models/dgps.py:25-35 via VariationalStrategy).
 //
-// Tiling: 128x128 CTA tile, BK = 16, 3-stage cp.async pipeline, 8 warps each owning a 64x32 warp tile = 8x4 DMMA tiles
-// (64 accumulator doubles per thread).  Shared-memory tiles are stored either K-contiguous [128][16+4] or MN-contiguous
-// [16][128+4], whichever matches the operand's global layout; with a leading dimension = 4 (mod 16) doubles both
-// fragment-load patterns are bank-conflict free for 64-bit accesses.
+// Tiling (templated): BK = 16, 3-stage cp.async pipeline, 8 warps per CTA.  Default "dual" configuration: 128x64 CTA
+// tile, 32x32 warp tiles (32 accumulator doubles per thread) so that TWO CTAs = 16 warps are resident per SM and one
+// CTA's barrier / address phase is covered by the other's DMMA stream; "big" configuration: 128x128 tile, 64x32 warp
+// tiles, one CTA per SM.  Shared-memory tiles are stored either K-contiguous [rows][16+4] or MN-contiguous
+// [16][cols+4], whichever matches the operand's global layout; with a leading dimension = 4 (mod 16) doubles both
+// fragment-load patterns are bank-conflict free for 64-bit accesses.  Chunk addresses are computed once per CTA; the
+// per-stage producer work is a pointer bump (plus a byte count at ragged edges).
 #include "common.cuh"
 
 namespace npgp {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, GEMM_THREADS = 256;
-constexpr int LDS_K = BK + 4;     // K-contiguous tile: [128][20]
-constexpr int LDS_MN = 128 + 4;   // MN-contiguous tile: [16][132]
-constexpr int TILE_DOUBLES = (128 * LDS_K > BK * LDS_MN) ? 128 * LDS_K : BK * LDS_MN;  // 2560
-constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES + BK;  // A tile, B tile, weights
-constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8;
+constexpr int GEMM_THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -36,36 +34,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
-}
-
-// K-contiguous operand: global G[row][k], leading dim ld.  Tile rows [row0,row0+128), k in [k0,k0+16).
-__device__ __forceinline__ void load_tile_kcontig(double* s, const double* __restrict__ G, long ld, int row0, int nrows,
-                                                  int k0, int kend) {
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c = threadIdx.x + GEMM_THREADS * it;
-    const int r = c >> 3, kc = (c & 7) * 2;
-    const int row = row0 + r, k = k0 + kc;
-    int bytes = 0;
-    if (row < nrows) bytes = max(0, min(2, kend - k)) * 8;
-    const double* src = bytes ? (G + (long)row * ld + k) : G;
-    cp_async16(s + r * LDS_K + kc, src, bytes);
-  }
-}
-
-// MN-contiguous operand: global G[k][col], leading dim ld.  Tile k in [k0,k0+16), cols [col0,col0+128).
-__device__ __forceinline__ void load_tile_mncontig(double* s, const double* __restrict__ G, long ld, int col0,
-                                                   int ncols, int k0, int kend) {
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int c = threadIdx.x + GEMM_THREADS * it;
-    const int kk = c >> 6, cc = (c & 63) * 2;
-    const int k = k0 + kk, col = col0 + cc;
-    int bytes = 0;
-    if (k < kend) bytes = max(0, min(2, ncols - col)) * 8;
-    const double* src = bytes ? (G + (long)k * ld + col) : G;
-    cp_async16(s + kk * LDS_MN + cc, src, bytes);
-  }
 }
 
 struct GemmParams {
@@ -86,8 +54,75 @@ struct GemmParams {
   double* q;
 };
 
-template <bool A_KCONTIG, bool B_KCONTIG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(GemmParams p) {
+// One operand tile of TR "rows" (the M or N extent) x BK, loaded with 16-byte cp.async.  A thread owns PASSES chunks
+// that differ by a uniform stride, so the steady-state producer work per stage is PASSES cp.async + one pointer bump;
+// only edge tiles and the ragged last k-step take the predicated path.
+template <int TR, int BK, bool KCONTIG>
+struct TileLoader {
+  static constexpr int LDS_K = BK + 4;                      // K-contiguous tile: [TR][BK+4], = 4 (mod 16)
+  static constexpr int LDMN = TR + 4;                       // MN-contiguous tile: [BK][TR+4], = 4 (mod 16)
+  static constexpr int TILE = KCONTIG ? TR * LDS_K : BK * LDMN;
+  static constexpr int PASSES = TR * BK / 2 / GEMM_THREADS;  // 16-byte chunks per thread
+  static constexpr int CPL = KCONTIG ? BK / 2 : TR / 2;      // chunks per tile line
+  static constexpr int LPP = GEMM_THREADS / CPL;             // tile lines covered per pass
+  static constexpr int SPASS = LPP * (KCONTIG ? LDS_K : LDMN);  // smem doubles between passes
+  const double* g;    // this thread's chunk of pass 0, at the current stage
+  const double* g0;   // operand base (always a valid address)
+  long pass_stride;   // global elements between passes
+  long stage_stride;  // global elements between stages
+  int soff;           // smem offset (doubles) of pass 0
+  int line, pos;      // tile line (row for K-contig, k for MN-contig) and position (k resp. column) of pass 0
+  int r0, nrows;
+
+  __device__ __forceinline__ void init(const double* __restrict__ G, long ld, int r0_, int nrows_, int kb) {
+    line = threadIdx.x / CPL;
+    pos = (threadIdx.x % CPL) * 2;
+    r0 = r0_;
+    nrows = nrows_;
+    g0 = G;
+    if (KCONTIG) {
+      g = G + (long)(r0 + line) * ld + kb + pos;
+      pass_stride = (long)LPP * ld;
+      stage_stride = BK;
+      soff = line * LDS_K + pos;
+    } else {
+      g = G + (long)(kb + line) * ld + r0 + pos;
+      pass_stride = (long)LPP * ld;
+      stage_stride = (long)BK * ld;
+      soff = line * LDMN + pos;
+    }
+  }
+  __device__ __forceinline__ void load_fast(double* s) {
+#pragma unroll
+    for (int it = 0; it < PASSES; ++it) cp_async16(s + soff + it * SPASS, g + it * pass_stride, 16);
+    g += stage_stride;
+  }
+  // predicated variant: k0 = absolute k of this stage, kend = exclusive bound of valid k
+  __device__ __forceinline__ void load_edge(double* s, int k0, int kend) {
+#pragma unroll
+    for (int it = 0; it < PASSES; ++it) {
+      int bytes;
+      if (KCONTIG) {
+        const bool row_ok = (r0 + line + it * LPP) < nrows;
+        bytes = row_ok ? max(0, min(2, kend - (k0 + pos))) * 8 : 0;
+      } else {
+        const bool k_ok = (k0 + line + it * LPP) < kend;
+        bytes = k_ok ? max(0, min(2, nrows - (r0 + pos))) * 8 : 0;
+      }
+      cp_async16(s + soff + it * SPASS, bytes ? g + it * pass_stride : g0, bytes);
+    }
+    g += stage_stride;
+  }
+};
+
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool A_KCONTIG, bool B_KCONTIG, bool HAS_W, int MINB>
+__global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p) {
+  using LA = TileLoader<BM, BK, A_KCONTIG>;
+  using LB = TileLoader<BN, BK, B_KCONTIG>;
+  constexpr int STAGE_DOUBLES = LA::TILE + LB::TILE + BK;
+  constexpr int MT = WM / 8, NT = WN / 8;
+  constexpr int WARPS_N = BN / WN;
+  static_assert((BM / WM) * WARPS_N == GEMM_THREADS / 32, "warp grid must cover the CTA tile");
   extern __shared__ __align__(16) double smem[];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (p.out_tri == 1 && n0 > m0 + BM - 1) return;
@@ -113,28 +148,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(GemmParams p) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
 
-  double acc[8][4][2];
+  double acc[MT][NT][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto load_stage = [&](int stage, int k0) {
-    double* sA = smem + stage * STAGE_DOUBLES;
-    double* sB = sA + TILE_DOUBLES;
-    double* sW = sB + TILE_DOUBLES;
-    if (A_KCONTIG) load_tile_kcontig(sA, p.A, p.lda, m0, p.M, k0, ke);
-    else load_tile_mncontig(sA, p.A, p.lda, m0, p.M, k0, ke);
-    if (B_KCONTIG) load_tile_kcontig(sB, p.B, p.ldb, n0, p.N, k0, ke);
-    else load_tile_mncontig(sB, p.B, p.ldb, n0, p.N, k0, ke);
-    if (p.w && tid < BK) sW[tid] = (k0 + tid < ke) ? p.w[k0 + tid] : 0.0;
+  LA la;
+  LB lb;
+  la.init(p.A, p.lda, m0, p.M, kb);
+  lb.init(p.B, p.ldb, n0, p.N, kb);
+  const bool full_mn = (m0 + BM <= p.M) && (n0 + BN <= p.N);
+  const int nk_fast = full_mn ? (ke - kb) / BK : 0;  // stages that need no predicate at all
+
+  // stages are issued strictly in order (0, 1, 2, ...), so the loaders just advance their pointers
+  auto load_stage = [&](int idx) {
+    double* sA = smem + (idx % STAGES) * STAGE_DOUBLES;
+    double* sB = sA + LA::TILE;
+    if (idx < nk_fast) {
+      la.load_fast(sA);
+      lb.load_fast(sB);
+    } else {
+      la.load_edge(sA, kb + idx * BK, ke);
+      lb.load_edge(sB, kb + idx * BK, ke);
+    }
+    if (HAS_W) {
+      double* sW = sB + LB::TILE;
+      const int k = kb + idx * BK + tid;
+      if (tid < BK) sW[tid] = (k < ke) ? p.w[k] : 0.0;
+    }
   };
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) load_stage(s, kb + s * BK);
+    if (s < nk) load_stage(s);
     cp_async_commit();
   }
   for (int kt = 0; kt < nk; ++kt) {
@@ -142,34 +191,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(GemmParams p) {
     __syncthreads();
     {
       const int nxt = kt + STAGES - 1;
-      if (nxt < nk) load_stage(nxt % STAGES, kb + nxt * BK);
+      if (nxt < nk) load_stage(nxt);
       cp_async_commit();
     }
     const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES;
-    const double* sB = sA + TILE_DOUBLES;
-    const double* sW = sB + TILE_DOUBLES;
+    const double* sB = sA + LA::TILE;
+    const double* sW = sB + LB::TILE;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double a[8], b[4];
+      double a[MT], b[NT];
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         const int m = wm0 + mt * 8 + g;
-        a[mt] = A_KCONTIG ? sA[m * LDS_K + kk + t4] : sA[(kk + t4) * LDS_MN + m];
+        a[mt] = A_KCONTIG ? sA[m * LA::LDS_K + kk + t4] : sA[(kk + t4) * LA::LDMN + m];
       }
-      if (p.w) {
+      if (HAS_W) {
         const double wk = sW[kk + t4];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) a[mt] *= wk;
+        for (int mt = 0; mt < MT; ++mt) a[mt] *= wk;
       }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int nt = 0; nt < NT; ++nt) {
         const int n = wn0 + nt * 8 + g;
-        b[nt] = B_KCONTIG ? sB[n * LDS_K + kk + t4] : sB[(kk + t4) * LDS_MN + n];
+        b[nt] = B_KCONTIG ? sB[n * LB::LDS_K + kk + t4] : sB[(kk + t4) * LB::LDMN + n];
       }
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < NT; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
   }
   cp_async_wait<0>();
@@ -177,11 +226,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(GemmParams p) {
   // epilogue
   const bool vec_c = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll
-  for (int mt = 0; mt < 8; ++mt) {
+  for (int mt = 0; mt < MT; ++mt) {
     const int row = m0 + wm0 + mt * 8 + g;
     double rowdot = 0.0;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
       const int col = n0 + wn0 + nt * 8 + 2 * t4;
       if (row < p.M && col < p.N) {
         const bool two = (col + 1 < p.N);
@@ -216,6 +265,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(GemmParams p) {
   }
 }
 
+// tile configurations (switchable at run time for A/B measurements, see npgp_set_gemm_config)
+struct Cfg0 { static constexpr int BM = 128, BN = 128, WM = 64, WN = 32, BK = 16, ST = 3, MINB = 1; };  // 1 CTA/SM
+struct Cfg1 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 16, ST = 3, MINB = 2; };   // 2 CTAs/SM
+struct Cfg2 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 32, ST = 2, MINB = 2; };
+struct Cfg3 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 16, ST = 4, MINB = 2; };
+struct Cfg4 { static constexpr int BM = 128, BN = 128, WM = 64, WN = 32, BK = 32, ST = 2, MINB = 1; };
+
+template <class Cfg, bool AK, bool BK_>
+constexpr int gemm_smem_bytes() {
+  return Cfg::ST * (TileLoader<Cfg::BM, Cfg::BK, AK>::TILE + TileLoader<Cfg::BN, Cfg::BK, BK_>::TILE + Cfg::BK) * 8;
+}
+
 __global__ void scale_matrix_kernel(int M, int N, double* C, long ldc, double beta, int out_tri) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)M * N) return;
@@ -234,23 +295,48 @@ __global__ void symmetrize_kernel(int M, double* C, long ldc, int from_upper) {
   else C[(long)r * ldc + c] = C[(long)c * ldc + r];
 }
 
-static int launch_gemm(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t st) {
+template <class Cfg, bool AK, bool BK_>
+static int launch_cfg(const GemmParams& p, cudaStream_t st) {
+  constexpr int smem = gemm_smem_bytes<Cfg, AK, BK_>();
+  auto kern = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, false, Cfg::MINB>;
+  auto kern_w = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, true, Cfg::MINB>;
   static bool attr_set = false;
   if (!attr_set) {
-    NPGP_CUDA(cudaFuncSetAttribute(dgemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    NPGP_CUDA(cudaFuncSetAttribute(dgemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    NPGP_CUDA(cudaFuncSetAttribute(dgemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    NPGP_CUDA(cudaFuncSetAttribute(dgemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    NPGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NPGP_CUDA(cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), p.splits);
-  if (a_kc && b_kc) dgemm_kernel<true, true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
-  else if (a_kc) dgemm_kernel<true, false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
-  else if (b_kc) dgemm_kernel<false, true><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
-  else dgemm_kernel<false, false><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
+  dim3 grid(ceil_div(p.N, Cfg::BN), ceil_div(p.M, Cfg::BM), p.splits);
+  if (p.w) kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
+  else kern<<<grid, GEMM_THREADS, smem, st>>>(p);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
+
+static int g_gemm_cfg = 1;
+
+template <class Cfg>
+static int launch_layout(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t st) {
+  if (a_kc && b_kc) return launch_cfg<Cfg, true, true>(p, st);
+  if (a_kc) return launch_cfg<Cfg, true, false>(p, st);
+  if (b_kc) return launch_cfg<Cfg, false, true>(p, st);
+  return launch_cfg<Cfg, false, false>(p, st);
+}
+
+static int launch_gemm(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t st) {
+  switch (g_gemm_cfg) {
+    case 0: return launch_layout<Cfg0>(a_kc, b_kc, p, st);
+    case 2: return launch_layout<Cfg2>(a_kc, b_kc, p, st);
+    case 3: return launch_layout<Cfg3>(a_kc, b_kc, p, st);
+    case 4: return launch_layout<Cfg4>(a_kc, b_kc, p, st);
+    default: return launch_layout<Cfg1>(a_kc, b_kc, p, st);
+  }
+}
+
+static int tile_bm() { return 128; }
+static int tile_bn() { return (g_gemm_cfg == 0 || g_gemm_cfg == 4) ? 128 : 64; }
+static int ctas_per_sm() { return (g_gemm_cfg == 0 || g_gemm_cfg == 4) ? 1 : 2; }
+constexpr int kMaxBK = 32;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -264,10 +350,10 @@ int dgemm_impl(int transA, int transB, int M, int N, int K, double alpha, const 
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.alpha = alpha; p.beta = beta; p.tri_a = tri_a; p.tri_b = tri_b; p.out_tri = out_tri; p.splits = 1;
   // small outputs with a long K: split K so that the 148 SMs have work
-  const long tiles = (long)ceil_div(M, BM) * ceil_div(N, BN);
-  if (tiles * 2 <= kNumSMs && K >= 8 * BK * 4) {
-    int s = (int)(kNumSMs / tiles);
-    s = min(s, K / (8 * BK));
+  const long tiles = (long)ceil_div(M, tile_bm()) * ceil_div(N, tile_bn());
+  if (tiles * 2 <= kNumSMs * ctas_per_sm() && K >= 8 * kMaxBK * 4) {
+    int s = (int)(kNumSMs * ctas_per_sm() / tiles);
+    s = min(s, K / (8 * kMaxBK));
     s = min(s, 16);
     if (s > 1) p.splits = s;
   }
@@ -313,10 +399,9 @@ extern "C" int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk,
   GemmParams p{};
   p.M = M; p.N = M; p.K = n; p.A = K; p.lda = ldk; p.B = K; p.ldb = ldk; p.C = Out; p.ldc = ldo;
   p.alpha = alpha; p.beta = 0.0; p.out_tri = 2; p.w = w;
-  const int tm = ceil_div(M, BM);
-  const long tiles = (long)tm * (tm + 1) / 2;
-  int s = (int)max(1L, (long)(2 * kNumSMs) / tiles / 2);
-  s = min(s, max(1, n / (16 * BK)));
+  const long tiles = ((long)ceil_div(M, tile_bm()) * ceil_div(M, tile_bn()) + ceil_div(M, tile_bm())) / 2;
+  int s = (int)max(1L, (long)(kNumSMs * ctas_per_sm()) / tiles);
+  s = min(s, max(1, n / (16 * kMaxBK)));
   p.splits = max(1, min(s, 32));
   if (p.splits > 1) {
     const long tot = (long)M * M;
@@ -336,5 +421,12 @@ extern "C" int npgp_symmetrize(int M, double* C, long ldc, int from_upper, cudaS
   dim3 blk(32, 8), grd(ceil_div(M, 32), ceil_div(M, 8));
   symmetrize_kernel<<<grd, blk, 0, stream>>>(M, C, ldc, from_upper);
   NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// measurement switch: 0 = 128x128 tiles (1 CTA/SM), 1 = 128x64 tiles (2 CTAs/SM, default)
+extern "C" int npgp_set_gemm_config(int cfg) {
+  if (cfg < 0 || cfg > 4) return NPGP_EINVAL;
+  npgp::g_gemm_cfg = cfg;
   return NPGP_OK;
 }

@@ -92,14 +92,18 @@ def main():
 
     Cm = torch.randn(M, M, **f64)
     T = torch.empty(B, M, **f64)
-    ms, best = timeit(lambda: ops.rowquad(K, Cm, T=T))
-    report("rowquad", ms, best, tflops=round(2 * B * M * M / best / 1e9, 2))
     Out = torch.empty(M, M, **f64)
-    ms, best = timeit(lambda: ops.wsyrk(K, None, out=Out))
-    report("wsyrk", ms, best, tflops_full=round(2 * B * M * M / best / 1e9, 2), tflops_useful=round(B * M * (M + 128) / best / 1e9, 2))
     A1, A2 = torch.randn(M, M, **f64), torch.randn(M, M, **f64)
-    ms, best = timeit(lambda: ops.dgemm(A1, A2, C=Out))
-    report("dgemm_MMM", ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
+    for cfg, nm in ((0, "128x128,bk16,s3"), (1, "128x64,bk16,s3"), (2, "128x64,bk32,s2"), (3, "128x64,bk16,s4"), (4, "128x128,bk32,s2")):
+        check(lib().npgp_set_gemm_config(cfg), "cfg")
+        ms, best = timeit(lambda: ops.rowquad(K, Cm, T=T))
+        report("rowquad[%s]" % nm, ms, best, tflops=round(2 * B * M * M / best / 1e9, 2))
+        ms, best = timeit(lambda: ops.wsyrk(K, None, out=Out))
+        report("wsyrk[%s]" % nm, ms, best, tflops_full=round(2 * B * M * M / best / 1e9, 2),
+               tflops_useful=round(B * M * (M + 128) / best / 1e9, 2))
+        ms, best = timeit(lambda: ops.dgemm(A1, A2, C=Out))
+        report("dgemm_MMM[%s]" % nm, ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
+    check(lib().npgp_set_gemm_config(1), "cfg")
     ms, best = timeit(lambda: torch.matmul(A1, A2, out=Out))
     report("cublas_dgemm_MMM(reference point)", ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
     ms, best = timeit(lambda: torch.matmul(K, Cm, out=T), iters=5)
