@@ -124,6 +124,21 @@ int npgp_adam_step(long n, double* p, const double* g, double* m, double* v, con
 int npgp_adam_step_dev(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
                        double beta1, double beta2, double eps, double* step_dev, double gscale, npgp_stream_t stream);
 
+/* ---- (d) doubly-stochastic deep GP (models/dgps.py:53-111 through GPyTorch DeepGPLayer.__call__ and
+ * DeepApproximateMLL(VariationalELBO)) ----------------------------------------------------
+ * Marginal reparameterised layer sample h = mu + sqrt(var) * eps over n elements.  eps_in NULL: eps ~ N(0,1) from
+ * Philox4x32-10 keyed by (seed, index_offset + element index) -- independent of how samples / rows are sharded;
+ * eps_out (may be NULL) receives the draws (needed by the backward). */
+int npgp_dsvi_sample(long n, const double* mu, const double* var, const double* eps_in, unsigned long long seed,
+                     unsigned long long index_offset, double* h, double* eps_out, npgp_stream_t stream);
+int npgp_dsvi_sample_bwd(long n, const double* var, const double* eps, const double* dh, double* dmu, double* dvar,
+                         npgp_stream_t stream);
+/* Per-sample Gaussian expected log-likelihood: mu, var (S,n), y (n); sums[s] += sum_i E log N(y_i | f_si, *noise)
+ * (warp-shuffle + block reduction); sq[s] += sum_i ((y-mu)^2 + var) (may be NULL); gmu, gvar (S,n) (may be NULL) =
+ * wscale * d/dmu, d/dvar of the per-element term. */
+int npgp_gauss_ell_batched(int S, int n, const double* y, const double* mu, const double* var, const double* noise,
+                           double wscale, double* sums, double* sq, double* gmu, double* gvar, npgp_stream_t stream);
+
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 

@@ -326,6 +326,84 @@ class RbfMatvecFn(torch.autograd.Function):
         return None, dz, None, None, dV if ctx.needs_input_grad[4] else None, None, None
 
 
+class RowquadFn(torch.autograd.Function):
+    """q_i = k_i^T C k_i for SYMMETRIC C (T = K C on the FP64 tensor pipe with the row-dot fused in the epilogue).
+    Backward: dK = 2 diag(dq) T,  dC = K^T diag(dq) K (wsyrk)."""
+
+    @staticmethod
+    def forward(ctx, K, Cm):
+        Kc, Cc = K.detach().contiguous(), Cm.detach().contiguous()
+        T, q = rowquad(Kc, Cc)
+        ctx.save_for_backward(Kc, T)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        K, T = ctx.saved_tensors
+        dK = (2.0 * dq).unsqueeze(-1) * T if ctx.needs_input_grad[0] else None
+        dC = wsyrk(K, dq.contiguous()) if ctx.needs_input_grad[1] else None
+        return dK, dC
+
+
+class DsviSampleFn(torch.autograd.Function):
+    """h = mu + sqrt(var) * eps (DeepGPLayer's Normal(mean, sqrt(variance)).rsample()); eps given or Philox-generated."""
+
+    @staticmethod
+    def forward(ctx, mu, var, eps, seed, offset):
+        muc, varc = mu.detach().contiguous(), var.detach().contiguous()
+        h = torch.empty_like(muc)
+        eps_out = torch.empty_like(muc) if eps is None else None
+        check(lib().npgp_dsvi_sample(muc.numel(), ptr(muc), ptr(varc), ptr(_c(eps)), int(seed), int(offset), ptr(h),
+                                     ptr(eps_out), stream()), "npgp_dsvi_sample")
+        ctx.save_for_backward(varc, eps_out if eps is None else _c(eps))
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        var, eps = ctx.saved_tensors
+        dh = dh.contiguous()
+        dmu, dvar = torch.empty_like(var), torch.empty_like(var)
+        check(lib().npgp_dsvi_sample_bwd(var.numel(), ptr(var), ptr(eps), ptr(dh), ptr(dmu), ptr(dvar), stream()),
+              "npgp_dsvi_sample_bwd")
+        return dmu, dvar, None, None, None
+
+
+class GaussEllBatchedFn(torch.autograd.Function):
+    """sums[s] = sum_i E_q log N(y_i | f_si, noise) for mu, var of shape (S, n); gradients to mu, var and noise."""
+
+    @staticmethod
+    def forward(ctx, y, mu, var, noise):
+        S, n = mu.shape
+        muc, varc, yc, nz = mu.detach().contiguous(), var.detach().contiguous(), y.detach().contiguous(), noise.detach()
+        sums = torch.zeros(S, dtype=torch.float64, device=mu.device)
+        sq = torch.zeros(S, dtype=torch.float64, device=mu.device)
+        gmu, gvar = torch.empty_like(muc), torch.empty_like(muc)
+        check(lib().npgp_gauss_ell_batched(S, n, ptr(yc), ptr(muc), ptr(varc), ptr(nz), 1.0, ptr(sums), ptr(sq),
+                                           ptr(gmu), ptr(gvar), stream()), "npgp_gauss_ell_batched")
+        ctx.save_for_backward(gmu, gvar, sq, nz)
+        ctx.n = n
+        return sums
+
+    @staticmethod
+    def backward(ctx, dsums):
+        gmu, gvar, sq, nz = ctx.saved_tensors
+        d = dsums.unsqueeze(-1)
+        dnoise = (dsums * 0.5 * (sq / (nz * nz) - ctx.n / nz)).sum().reshape(nz.shape)
+        return None, d * gmu, d * gvar, dnoise
+
+
+def rowquad_sym(K, Cm):
+    return RowquadFn.apply(K, Cm)
+
+
+def dsvi_sample(mu, var, eps=None, seed=0, offset=0):
+    return DsviSampleFn.apply(mu, var, eps, seed, offset)
+
+
+def gauss_ell_batched(y, mu, var, noise):
+    return GaussEllBatchedFn.apply(y, mu, var, noise)
+
+
 def gibbs_diag(x1, ell1, x2, ell2, scale=None):
     return GibbsDiagFn.apply(x1, ell1, x2, ell2, scale)
 
