@@ -143,8 +143,9 @@ __device__ __forceinline__ void acc_axpy_global(const double (&acc)[2][4][2], do
 // per thread, the trailing update one element per thread.  The inverse is then assembled by recursive doubling
 // (8 -> 16 -> 32 -> 64) with element-per-thread products.  tmp: >= 32*32 doubles.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void chol8_serial(double* s, double* x, int c0, int global_offset, int* __restrict__ info) {
-  double a[8][8], xi[8][8], inv[8];
+__device__ __forceinline__ void chol8_serial(double* s, double* sInv, int c0, int global_offset,
+                                             int* __restrict__ info) {
+  double a[8][8], inv[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -163,29 +164,36 @@ __device__ __forceinline__ void chol8_serial(double* s, double* x, int c0, int g
       for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int r = 0; r < 8; ++r) {
+    sInv[c0 + r] = inv[r];
 #pragma unroll
-    for (int r = c; r < 8; ++r) {
-      double acc = (r == c) ? 1.0 : 0.0;
+    for (int c = 0; c < 8; ++c) s[(c0 + r) * TLD + c0 + c] = (c <= r) ? a[r][c] : 0.0;
+  }
+}
+
+// column c (0..7) of the inverse of the 8x8 lower block at (c0,c0), by forward substitution; one thread per column
+__device__ __forceinline__ void inv8_column(const double* s, const double* sInv, double* x, int c0, int c) {
+  double xc[8];
 #pragma unroll
-      for (int k = c; k < r; ++k) acc = fma(-a[r][k], xi[k][c], acc);
-      xi[r][c] = acc * inv[r];
-    }
+  for (int r = 0; r < 8; ++r) {
+    double acc = (r == c) ? 1.0 : 0.0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
+    for (int k = 0; k < r; ++k) acc = fma(-s[(c0 + r) * TLD + c0 + k], (k >= c) ? xc[k] : 0.0, acc);
+    xc[r] = (r >= c) ? acc * sInv[c0 + r] : 0.0;
+  }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      s[(c0 + r) * TLD + c0 + c] = (c <= r) ? a[r][c] : 0.0;
-      x[(c0 + r) * TLD + c0 + c] = (c <= r) ? xi[r][c] : 0.0;
-    }
+  for (int r = 0; r < 8; ++r) x[(c0 + r) * TLD + c0 + c] = xc[r];
 }
 
 __device__ void factor_invert_64(double* s, double* x, double* tmp, int global_offset, int* __restrict__ info) {
   const int tid = threadIdx.x;
+  double* sInv = tmp + 32 * 32;  // 64 reciprocal pivots (tmp holds >= 64*68 doubles)
   for (int e = tid; e < TB * TB; e += CT) x[(e >> 6) * TLD + (e & 63)] = 0.0;
   __syncthreads();
   for (int c0 = 0; c0 < TB; c0 += 8) {
-    if (tid == 0) chol8_serial(s, x, c0, global_offset, info);
+    if (tid == 0) chol8_serial(s, sInv, c0, global_offset, info);
+    __syncthreads();
+    if (tid < 8) inv8_column(s, sInv, x, c0, tid);
     __syncthreads();
     const int r1 = c0 + 8, n = TB - r1;
     // panel: row r of L[:, c0:c0+8] = A[r, c0:c0+8] * X8^T  (X8 lower: X8[c][k], k <= c)

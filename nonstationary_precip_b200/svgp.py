@@ -276,11 +276,17 @@ class SVGPGibbs:
 
         # ---- backward of the data term through K(X_B, Z)
         gv2 = 2.0 * gv
-        with self._fork():  # side stream: reductions over rows, then the O(M^3) backward chain u, C -> m, Ls, Kzz
+        # Scheduling (all FP64 work shares one pipe, DFMA and DMMA alike): the SYRK runs alone at full rate on the side
+        # stream; the latency-bound O(M^3) backward chain that follows it is then hidden under the FP64-bound Gibbs
+        # backward on the main stream, which starts when the SYRK has finished.
+        wsyrk_done = torch.cuda.Event() if (self._side is not None and self.overlap) else None
+        with self._fork():
             with self._sec("colwsum"):
                 du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
                 dC = o.wsyrk(K, w=gv)
+            if wsyrk_done is not None:
+                wsyrk_done.record()
             with self._sec("m3_bwd+kzz_bwd"):
                 dm = o.gemv_n(P, du)
                 dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
@@ -294,26 +300,23 @@ class SVGPGibbs:
                 g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
                 dfz1, dfz2, dZ1, dZ2, ds2 = self._kernel_bwd(Z, fz, Z, fz, s, G=dKzz, need_dx1=self.learn_z,
                                                              need_dx2=self.learn_z, need_dscale=True)
+        if wsyrk_done is not None:
+            torch.cuda.current_stream().wait_event(wsyrk_done)
         with self._sec("kxz_bwd"):
             dfx, dfz, _, dZ, ds = self._kernel_bwd(xb, fx, Z, fz, s, G=T, rowscale=gv2, rowvec=gmu, colvec=u,
                                                    need_dx2=self.learn_z, need_dscale=True)
         ds = ds + gv.sum()  # v = s + ...
-        self._join()
-        sec_m3 = self._sec("field_bwd+assemble")
-        sec_m3.__enter__()
-        dfz = dfz + dfz1 + dfz2
-        ds = ds + ds2
-        gZ = torch.zeros_like(Z)
-        if self.learn_z:
-            gZ += dZ + dZ1 + dZ2
 
-        # ---- backward through the field interpolation
+        # ---- backward through the field interpolation: the row-side part needs only dfx (main stream, before the join)
+        sec_f = self._sec("field_bwd")
+        sec_f.__enter__()
+        gZ = torch.zeros_like(Z)
         if self.variant == "diag":
             alpha, ell_x, ell_z = fc["alpha"], fc["ell_x"], fc["ell_z"]
             dlog = (dfx * ell_x).unsqueeze(-1)
             dalpha, dZf = o.rbf_matvec_bwd(xb, Z, self.prior_lam, self.prior_os, alpha.unsqueeze(-1), dlog,
                                            need_dz=self.learn_z)
-            g_logell = dfz * ell_z
+            g_logell = torch.zeros_like(ell_z)
             for b in range(d):
                 Pb = fc["Ps"][b]
                 beta = self._solve_spd(Pb, dalpha[b, :, 0])
@@ -324,25 +327,21 @@ class SVGPGibbs:
                 if self.learn_z:
                     lamb = self._bcast_ell(self.prior_lam[b], M)
                     # dELBO/dKp_b = -beta alpha^T  (+ prior: pw (0.5 alpha alpha^T - 0.5 Kp^-1))
-                    Gm = rs = None
+                    Gm = None
                     rv, cv = -beta, alpha[b]
                     if self.include_prior:
                         Gm = o.dgemm(Pb, Pb, transA=True, alpha=-0.5 * pw, tri_a=2, tri_b=1)
                         rv = rv + 0.5 * pw * alpha[b]
-                    r = o.gibbs_diag_bwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1], G=Gm, rowscale=rs, rowvec=rv,
-                                         colvec=cv, need_dx1=True, need_dx2=True)
+                    r = o.gibbs_diag_bwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1], G=Gm, rowvec=rv, colvec=cv,
+                                         need_dx1=True, need_dx2=True)
                     gZ += r["d_x1"] + r["d_x2"]
             if self.learn_z:
                 gZ += dZf
-            g["log_ell_z"].copy_(-g_logell)
         else:
             dHx, dD1 = o.sigma_from_h_bwd(fc["Hx"], p["D"], dfx)
             dW, dZf = o.rbf_matvec_bwd(xb, Z, self.row_lam, self.row_os, fc["W"].unsqueeze(0), dHx.unsqueeze(0),
                                        need_dz=self.learn_z)
             beta = self._solve_spd(fc["Pr"], dW[0])  # (M,d) = Kr^-1 dW
-            dHz, dD2 = o.sigma_from_h_bwd(p["H"], p["D"], dfz)
-            g["H"].copy_(-(beta + dHz))
-            g["D"].copy_(-(dD1 + dD2))
             if self.learn_z:
                 kp = 4
                 b4 = torch.zeros(M, kp, dtype=torch.float64, device=self.dev)
@@ -351,6 +350,22 @@ class SVGPGibbs:
                 Gk = o.dgemm(b4, w4, transB=True, alpha=-1.0)  # dELBO/dKr = -beta W^T
                 r = o.gibbs_diag_bwd(Z, fc["lamr"], Z, fc["lamr"], self.row_os, G=Gk, need_dx1=True, need_dx2=True)
                 gZ += dZf + r["d_x1"] + r["d_x2"]
+        sec_f.__exit__()
+
+        # ---- join the O(M^3) chain and assemble the flat gradient
+        self._join()
+        sec_m3 = self._sec("assemble")
+        sec_m3.__enter__()
+        dfz = dfz + dfz1 + dfz2
+        ds = ds + ds2
+        if self.learn_z:
+            gZ += dZ + dZ1 + dZ2
+        if self.variant == "diag":
+            g["log_ell_z"].copy_(-(g_logell + dfz * ell_z))
+        else:
+            dHz, dD2 = o.sigma_from_h_bwd(p["H"], p["D"], dfz)
+            g["H"].copy_(-(beta + dHz))
+            g["D"].copy_(-(dD1 + dD2))
         g["Z"].copy_(-gZ)
         g["raw_outputscale"].copy_(-(ds * torch.sigmoid(p["raw_outputscale"])).reshape(1))
         dnoise = (0.5 / Bg) * (acc[1] / (noise * noise) - Bl / noise)
