@@ -139,6 +139,14 @@ int npgp_dsvi_sample_bwd(long n, const double* var, const double* eps, const dou
 int npgp_gauss_ell_batched(int S, int n, const double* y, const double* mu, const double* var, const double* noise,
                            double wscale, double* sums, double* sq, double* gmu, double* gvar, npgp_stream_t stream);
 
+/* ---- temporal kernel of the spatio-temporal model (models/spatio_temporal_models.py:42):
+ * K[i,j] = s exp(-0.5 tau^2/l_r^2) exp(-2 sin^2(pi |tau|/p)/l_p), tau = t1[i] - t2[j]; hyp (device) = [l_r, l_p, p, s].
+ * Backward: out4 += dL/d[l_r, l_p, p, s]; dt2 (n2, may be NULL) += dL/dt2. */
+int npgp_rbfper_fwd(int n1, int n2, const double* t1, const double* t2, const double* hyp, double* K, long ldk,
+                    npgp_stream_t stream);
+int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const double* hyp, const double* G, long ldg,
+                    double* out4, double* dt2, npgp_stream_t stream);
+
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 

@@ -378,3 +378,122 @@ class ExactMarginalLogLikelihood(Module):
         for _, module, prior, closure in self.model.named_priors():
             res = res + prior.log_prob(closure(module)).sum()
         return res / target.shape[-1]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# stationary kernels of the spatio-temporal model (models/spatio_temporal_models.py:41-44)
+# ----------------------------------------------------------------------------------------------------------------------
+class PeriodicKernel(Kernel):
+    """exp(-2 sin^2(pi |x - x'| / p) / l)  (GPyTorch <= 1.8 convention); 1-D inputs."""
+
+    def __init__(self, active_dims=None, **kwargs):
+        super().__init__(None, torch.Size([]), active_dims)
+        self.raw_lengthscale = torch.nn.Parameter(torch.zeros(1, 1))
+        self.raw_period_length = torch.nn.Parameter(torch.zeros(1, 1))
+
+    @property
+    def lengthscale(self):
+        return softplus(self.raw_lengthscale)
+
+    @property
+    def period_length(self):
+        return softplus(self.raw_period_length)
+
+    def forward(self, x1, x2, diag=False, **params):
+        one = torch.ones(1, dtype=x1.dtype, device=x1.device)
+        hyp = torch.cat([1e150 * one, self.lengthscale.reshape(1), self.period_length.reshape(1), one])
+        from . import ops
+        return ops.rbf_periodic(x1[:, 0], x2[:, 0], hyp)
+
+
+class ProductKernel(Kernel):
+    """RBFKernel * PeriodicKernel on the same single dimension, evaluated in one fused kernel."""
+
+    def __init__(self, k1, k2):
+        super().__init__()
+        self.kernels = torch.nn.ModuleList([k1, k2])
+        if not (isinstance(k1, RBFKernel) and isinstance(k2, PeriodicKernel)):
+            raise NotImplementedError("only RBFKernel * PeriodicKernel is on the hot path")
+
+    def hyper(self, outputscale):
+        rbf, per = self.kernels
+        return torch.cat([rbf.lengthscale.reshape(-1)[:1], per.lengthscale.reshape(1), per.period_length.reshape(1),
+                          outputscale.reshape(1)])
+
+    def forward(self, x1, x2, diag=False, outputscale=None, **params):
+        from . import ops
+        os = outputscale if outputscale is not None else torch.ones(1, dtype=x1.dtype, device=x1.device)
+        return ops.rbf_periodic(x1[:, 0], x2[:, 0], self.hyper(os))
+
+
+def _kernel_mul(self, other):
+    return ProductKernel(self, other)
+
+
+def _kernel_add(self, other):
+    return AdditiveKernel(self, other)
+
+
+Kernel.__mul__ = _kernel_mul
+Kernel.__add__ = _kernel_add
+
+
+class AdditiveKernel(Kernel):
+    """Sum of kernels; low-rank-root summands are merged into one root [R1 R2] (rank M1 + M2)."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        self.kernels = torch.nn.ModuleList(kernels)
+
+    def forward(self, x1, x2, diag=False, **params):
+        parts = [k(x1, x2, diag=diag, **params) for k in self.kernels]
+        return sum_covariances(parts)
+
+
+def sum_covariances(parts):
+    if all(isinstance(p, LowRankRootCovar) for p in parts):
+        root = torch.cat([p.root for p in parts], dim=-1)
+        diags = [p.added_diag for p in parts if p.added_diag is not None]
+        return LowRankRootCovar(root, sum(diags) if diags else None)
+    dense = [p.evaluate() if isinstance(p, LowRankRootCovar) else p for p in parts]
+    return sum(dense)
+
+
+class InducingPointKernel(Kernel):
+    """gpytorch.kernels.InducingPointKernel restated: root K_xz Kzz^{-1/2}, eval-time diagonal
+    correction, training-time added loss term; used for the temporal part (spatio_temporal_models.py:42-44)."""
+
+    def __init__(self, base_kernel, inducing_points, likelihood, active_dims=None):
+        super().__init__(active_dims=active_dims)
+        self.base_kernel, self.likelihood = base_kernel, likelihood
+        if inducing_points.dim() == 1:
+            inducing_points = inducing_points.unsqueeze(-1)
+        # like upstream: re-wrapped in a new Parameter (aliases the storage of the tensor it was given)
+        self.register_parameter("inducing_points", torch.nn.Parameter(inducing_points.data
+                                                                     if isinstance(inducing_points, torch.nn.Parameter)
+                                                                     else inducing_points))
+
+    def _base(self, a, b):
+        return self.base_kernel(a, b)
+
+    def forward(self, x1, x2, diag=False, **params):
+        z = self.inducing_points
+        Kzz = self._base(z, z)
+        _, P = F.psd_safe_chol_inv(Kzz)
+        inv_root = P.T
+        root1 = F.matmul(self._base(x1, z), inv_root)
+        if torch.equal(x1, x2):
+            covar = LowRankRootCovar(root1)
+            prior_diag = self.base_kernel(x1, x1, diag=True)
+            if self.training:
+                self.update_added_loss_term("inducing_point_loss_term",
+                                            InducingPointKernelAddedLossTerm(prior_diag, covar.diag(), self.likelihood))
+            else:
+                covar = LowRankRootCovar(root1, (prior_diag - covar.diag()).clamp(0, math.inf))
+        else:
+            if self.training:
+                raise RuntimeError("x1 should equal x2 in training mode")
+            covar = F.matmul(root1, F.matmul(self._base(x2, z), inv_root).T)
+        if diag:
+            return covar.diag() if isinstance(covar, LowRankRootCovar) else torch.diagonal(covar)
+        return covar

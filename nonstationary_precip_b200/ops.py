@@ -392,6 +392,34 @@ class GaussEllBatchedFn(torch.autograd.Function):
         return None, d * gmu, d * gvar, dnoise
 
 
+class RbfPerFn(torch.autograd.Function):
+    """K = s * RBF(t1,t2) * Periodic(t1,t2) on 1-D inputs; hyp = [l_rbf, l_per, period, s] (4,).  Gradients to hyp, t2."""
+
+    @staticmethod
+    def forward(ctx, t1, t2, hyp):
+        t1c, t2c, hc = t1.detach().contiguous().reshape(-1), t2.detach().contiguous().reshape(-1), hyp.detach().contiguous()
+        K = torch.empty(t1c.numel(), t2c.numel(), dtype=torch.float64, device=t1.device)
+        check(lib().npgp_rbfper_fwd(t1c.numel(), t2c.numel(), ptr(t1c), ptr(t2c), ptr(hc), ptr(K), K.stride(0), stream()),
+              "npgp_rbfper_fwd")
+        ctx.save_for_backward(t1c, t2c, hc)
+        ctx.t2_shape = t2.shape
+        return K
+
+    @staticmethod
+    def backward(ctx, G):
+        t1, t2, hyp = ctx.saved_tensors
+        G = G.contiguous()
+        out4 = torch.zeros(4, dtype=torch.float64, device=G.device)
+        dt2 = torch.zeros_like(t2) if ctx.needs_input_grad[1] else None
+        check(lib().npgp_rbfper_bwd(t1.numel(), t2.numel(), ptr(t1), ptr(t2), ptr(hyp), ptr(G), G.stride(0), ptr(out4),
+                                    ptr(dt2), stream()), "npgp_rbfper_bwd")
+        return None, (dt2.reshape(ctx.t2_shape) if dt2 is not None else None), out4
+
+
+def rbf_periodic(t1, t2, hyp):
+    return RbfPerFn.apply(t1, t2, hyp)
+
+
 def rowquad_sym(K, Cm):
     return RowquadFn.apply(K, Cm)
 

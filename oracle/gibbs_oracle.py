@@ -417,3 +417,66 @@ def dgp_elbo(x, y, N_total, layers, last, raw_noise, eps, jitter_zz=1e-6):
         for o in range(lay["Z"].shape[0]):
             kl = kl + kl_whitened(lay["m"][o], torch.tril(lay["Ls"][o]))
     return (ell - kl / N_total).mean()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Spatio-temporal sparse model (models/spatio_temporal_models.py:35-126)
+# ----------------------------------------------------------------------------------------------------------------------
+def _nystrom_root(Kxz, Kzz):
+    """K_xz U^-1 with Kzz = U^T U (gibbs_kernels.py:197-225 / gpytorch InducingPointKernel)."""
+    L = psd_cholesky(Kzz)
+    return torch.linalg.solve_triangular(L, Kxz.T, upper=False).T
+
+
+def st_roots(x, Z, log_ell_z, hyp_t, os_s, prior_c, prior_os, prior_lam):
+    """Low-rank roots of the temporal (RBF x Periodic on column 0, outputscale hyp_t[3]) and spatial (Gibbs on columns
+    1,2, outputscale os_s) Nystrom kernels on the shared inducing points Z (M,3)."""
+    lr, lp, per, os_t = hyp_t
+    xt, zt, xs, zs = x[:, :1], Z[:, :1], x[:, 1:3], Z[:, 1:3]
+    kt = lambda a, b: os_t * rbf_ard_K(a, b, lr.reshape(1)) * periodic_K(a, b, lp, per)  # noqa: E731
+    Rt = _nystrom_root(kt(xt, zt), kt(zt, zt))
+    ell_z = torch.exp(log_ell_z)
+    ell_x = field_interp_diag(xs, zs, ell_z, prior_c, prior_os, prior_lam)
+    Rs_u = _nystrom_root(gibbs_diag_K(xs, zs, ell_x, ell_z), gibbs_diag_K(zs, zs, ell_z, ell_z))
+    return Rt, torch.sqrt(os_s) * Rs_u, Rs_u
+
+
+def st_sgpr_objective(x, y, Z, log_ell_z, hyp_t, os_s, noise, prior_c, prior_os, prior_lam):
+    """ExactMarginalLogLikelihood of SparseSpatioTemporal_Nonstationary in training mode (SURVEY 3.2 applied to the sum of
+    the two Nystrom kernels): [log N(y|0, R R^T + noise I) + both trace terms + log-prior] / n."""
+    n = x.shape[0]
+    Rt, Rs, Rs_u = st_roots(x, Z, log_ell_z, hyp_t, os_s, prior_c, prior_os, prior_lam)
+    R = torch.cat([Rt, Rs], -1)
+    k = R.shape[1]
+    Bm = torch.eye(k, dtype=x.dtype) + R.T @ R / noise
+    LB = psd_cholesky(Bm)
+    w = torch.linalg.solve_triangular(LB, (R.T @ y).unsqueeze(-1), upper=False).squeeze(-1)
+    quad = (y * y).sum() / noise - (w * w).sum() / noise ** 2
+    logdet = 2.0 * torch.log(torch.diagonal(LB)).sum() + n * torch.log(noise)
+    ll = -0.5 * (quad + logdet + n * LOG2PI)
+    trace_t = -0.5 * (hyp_t[3] - (Rt * Rt).sum(-1)).sum() / noise
+    trace_s = -0.5 * (1.0 - (Rs_u * Rs_u).sum(-1)).sum() / noise
+    lp = lognormal_prior_log_prob(Z[:, 1:3], log_ell_z, prior_c, prior_os, prior_lam).sum()
+    return (ll + trace_t + trace_s + lp) / n
+
+
+def st_predict(x, y, Z, log_ell_z, x_new, hyp_t, os_s, noise, prior_c, prior_os, prior_lam, literal=True):
+    """SparseSpatioTemporal_Nonstationary.predict in eval mode.  literal=True reproduces the reference's arithmetic
+    (spatio_temporal_models.py:101-123: rows of the DENSE joint covariance used as the factors L and A^T);
+    literal=False uses the concatenated low-rank root."""
+    n = x.shape[0]
+    xa = torch.cat([x, x_new], 0)
+    Rt, Rs, Rs_u = st_roots(xa, Z, log_ell_z, hyp_t, os_s, prior_c, prior_os, prior_lam)
+    R = torch.cat([Rt, Rs], -1)
+    corr = (hyp_t[3] - (Rt * Rt).sum(-1)).clamp_min(0.0) + os_s * (1.0 - (Rs_u * Rs_u).sum(-1)).clamp_min(0.0)
+    dense = R @ R.T + torch.diag(corr)
+    if literal:
+        L, At = dense[n:, :], dense[:n, :] / torch.sqrt(noise)
+    else:
+        L, At = R[n:], R[:n] / torch.sqrt(noise)
+    k = At.shape[1]
+    Bm = torch.eye(k, dtype=x.dtype) + At.T @ At
+    Binv = torch.linalg.inv(Bm)
+    mean = L @ (Binv @ (At.T @ y)) / torch.sqrt(noise)
+    covar = dense[n:, n:] - L @ (torch.eye(k, dtype=x.dtype) - Binv) @ L.T
+    return mean, covar

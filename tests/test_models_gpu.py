@@ -155,3 +155,58 @@ def test_multivariate_kernel_golden_and_gradients(golden):
     Dc = g["Dm"].clone().requires_grad_(True)
     o.gibbs_full_K(g["x1"], g["x2"], o.sigma_from_H(g["H1"], Dc), o.sigma_from_H(g["H2"], Dc)).sum().backward()
     assert rel(k.D.grad, Dc.grad) < 1e-9
+
+
+def test_spatio_temporal_nonstationary_objective_and_predict():
+    """SparseSpatioTemporal_Nonstationary (reference models/spatio_temporal_models.py:35-126) vs the oracle: training
+    objective, gradients (lengthscale field, spatial Z, temporal hyper-parameters) and both predict variants."""
+    from nonstationary_precip_b200.gp_base import ExactMarginalLogLikelihood, GaussianLikelihood
+    from nonstationary_precip_b200.models.spatio_temporal_models import SparseSpatioTemporal_Nonstationary
+    g = torch.Generator().manual_seed(8)
+    n, ns, M = 172, 43, 40
+    t = torch.sort(torch.rand(n + ns, generator=g) * 4 - 2)[0]
+    xy = torch.rand(n + ns, 2, generator=g) * 2 - 1
+    xa = torch.cat([t[:, None], xy], 1)
+    perm = torch.randperm(n + ns, generator=g)
+    x, xs = xa[perm[:n]], xa[perm[n:]]
+    y = torch.sin(2 * math.pi * x[:, 0]) * torch.exp(-x[:, 1] ** 2) + 0.1 * torch.randn(n, generator=g)
+    z = x[torch.randperm(n, generator=g)[:M]].clone()
+    prior = make_prior(2)
+    lik = GaussianLikelihood().cuda().double()
+    model = SparseSpatioTemporal_Nonstationary(x.cuda(), y.cuda(), lik, prior, z.cuda(), num_dim=2).cuda().double()
+    model.likelihood.noise = 0.05
+    model.spatial_covar_module.outputscale = 0.8
+    with torch.no_grad():
+        model.log_ell_z += 0.2 * torch.randn(2, M, generator=g).cuda()
+    tk = model.temporal_covar_module.base_kernel
+    mll = ExactMarginalLogLikelihood(lik, model)
+    model.train()
+    loss = -mll(model(model.train_inputs[0]), model.train_targets)
+    loss.backward()
+
+    c, os_, lam = torch.full((2,), math.log(0.3)), torch.ones(2), torch.full((2, 2), 1.3)
+    le = model.log_ell_z.detach().cpu().clone().requires_grad_(True)
+    zc = z.clone().requires_grad_(True)
+    hyp = tk.base_kernel.hyper(tk.outputscale).detach().cpu().clone().requires_grad_(True)
+    want = -o.st_sgpr_objective(x, y, zc, le, hyp, torch.tensor(0.8), torch.tensor(0.05), c, os_, lam)
+    want.backward()
+    assert abs(loss.item() - want.item()) < 1e-8 * abs(want.item())
+    assert rel(model.log_ell_z.grad, le.grad) < 1e-5
+    # spatial columns of Z are trainable; the temporal alias is frozen (spatio_temporal_models.py:44)
+    gz = model.spatial_covar_module.base_kernel.inducing_points.grad
+    assert rel(gz[:, 1:], zc.grad[:, 1:]) < 1e-5
+    assert model.temporal_covar_module.inducing_points.grad is None
+    # chain rule through softplus for the temporal hyper-parameters
+    rbf, per = tk.base_kernel.kernels
+    assert rel(rbf.raw_lengthscale.grad.reshape(()), hyp.grad[0] * torch.sigmoid(rbf.raw_lengthscale.detach().cpu()).reshape(())) < 1e-6
+    assert rel(per.raw_period_length.grad.reshape(()), hyp.grad[2] * torch.sigmoid(per.raw_period_length.detach().cpu()).reshape(())) < 1e-6
+    assert rel(tk.raw_outputscale.grad.reshape(()), hyp.grad[3] * torch.sigmoid(tk.raw_outputscale.detach().cpu()).reshape(())) < 1e-6
+
+    model.eval()
+    for literal in (True, False):
+        with torch.no_grad():
+            pred = model.predict(xs.cuda(), literal=literal)
+        mu, cov = o.st_predict(x, y, z, le.detach(), xs, hyp.detach(), torch.tensor(0.8), torch.tensor(0.05), c, os_,
+                               lam, literal=literal)
+        assert rel(pred.mean, mu) < 1e-6, literal
+        assert rel(pred.covariance_matrix, cov) < 1e-6, literal
