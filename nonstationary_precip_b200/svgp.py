@@ -186,16 +186,14 @@ class SVGPGibbs:
         if self._side is not None and self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
 
-    def _field_forward(self, x, fz=None):
-        """Latent field interpolated from Z to the rows x.  Returns (fz, fx, cache)."""
+    def _field_prepare(self, fz):
+        """Z-side part of the field interpolation (independent of the rows): the prior-kernel factorisations at Z and
+        the interpolation weights (alpha for the log-normal field, W = (K_row + 1e-5 I)^-1 H for the matrix field)."""
         o, p, M, d = self.o, self.p, self.M, self.d
         Z = p["Z"]
         c = {}
-        if fz is None:
-            fz = self._field_z()
         if self.variant == "diag":
-            ell_z = fz
-            alphas, Ps, Linvdiag = [], [], []
+            alphas, Ps, Ldiag = [], [], []
             for b in range(d):
                 lamb = self._bcast_ell(self.prior_lam[b], M)
                 Kp = o.gibbs_diag_fwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1])
@@ -203,22 +201,34 @@ class SVGPGibbs:
                 Lb, Pb, _ = o.potrf_inv(Kp, overwrite=True)
                 alphas.append(self._solve_spd(Pb, p["log_ell_z"][b] - self.prior_c[b]))
                 Ps.append(Pb)
-                Linvdiag.append(torch.diagonal(Lb).clone())
-            alpha = torch.stack(alphas)  # (D,M)
-            ell_x = o.rbf_matvec_fwd(x, Z, self.prior_lam, self.prior_os, alpha.unsqueeze(-1), bias=self.prior_c,
-                                     apply_exp=True).squeeze(-1)
-            c.update(alpha=alpha, Ps=Ps, Ldiag=Linvdiag, ell_z=ell_z, ell_x=ell_x)
-            return ell_z, ell_x, c
-        Sz = fz
-        lamr = self._bcast_ell(self.row_lam[0], M)
-        Kr = o.gibbs_diag_fwd(Z, lamr, Z, lamr, self.row_os)
-        Kr.diagonal().add_(1e-5)
-        _, Pr, _ = o.potrf_inv(Kr, overwrite=True)
-        W = self._solve_spd(Pr, p["H"])  # (M,d)
-        Hx = o.rbf_matvec_fwd(x, Z, self.row_lam, self.row_os, W.unsqueeze(0))[0]  # (B,d)
-        Sx = o.sigma_from_h_fwd(Hx, p["D"])
-        c.update(Pr=Pr, W=W, Hx=Hx, lamr=lamr)
-        return Sz, Sx, c
+                Ldiag.append(torch.diagonal(Lb).clone())
+            c.update(alpha=torch.stack(alphas), Ps=Ps, Ldiag=Ldiag, ell_z=fz)
+        else:
+            lamr = self._bcast_ell(self.row_lam[0], M)
+            Kr = o.gibbs_diag_fwd(Z, lamr, Z, lamr, self.row_os)
+            Kr.diagonal().add_(1e-5)
+            _, Pr, _ = o.potrf_inv(Kr, overwrite=True)
+            c.update(Pr=Pr, W=self._solve_spd(Pr, p["H"]), lamr=lamr)
+        return c
+
+    def _field_apply(self, x, c):
+        """Row-side part: the field interpolated to the rows x (matrix free).  Returns fx; adds Hx / ell_x to the cache."""
+        o, p = self.o, self.p
+        if self.variant == "diag":
+            ell_x = o.rbf_matvec_fwd(x, p["Z"], self.prior_lam, self.prior_os, c["alpha"].unsqueeze(-1),
+                                     bias=self.prior_c, apply_exp=True).squeeze(-1)
+            c["ell_x"] = ell_x
+            return ell_x
+        Hx = o.rbf_matvec_fwd(x, p["Z"], self.row_lam, self.row_os, c["W"].unsqueeze(0))[0]  # (B,d)
+        c["Hx"] = Hx
+        return o.sigma_from_h_fwd(Hx, p["D"])
+
+    def _field_forward(self, x, fz=None):
+        """Latent field interpolated from Z to the rows x.  Returns (fz, fx, cache)."""
+        if fz is None:
+            fz = self._field_z()
+        c = self._field_prepare(fz)
+        return fz, self._field_apply(x, c), c
 
     def _zz_forward(self, fz, s):
         o, p, M = self.o, self.p, self.M
@@ -433,18 +443,25 @@ class SVGPGibbs:
 
     @torch.no_grad()
     def predict(self, xs, chunk: int = 1 << 18):
-        """Posterior marginal mean and variance of f at xs (rows can be sharded across ranks by the caller)."""
+        """Posterior marginal mean and variance of f at xs (rows can be sharded across ranks by the caller; no
+        collective is involved).  Z-side factors are computed once, rows are streamed in chunks."""
         o, p = self.o, self.p
         s = _softplus(p["raw_outputscale"])
-        means, variances = [], []
-        zz = None
-        for lo in range(0, xs.shape[0], chunk):
+        fz = self._field_z()
+        fc = self._field_prepare(fz)
+        zz = self._zz_forward(fz, s)
+        n = xs.shape[0]
+        mean = torch.empty(n, dtype=torch.float64, device=self.dev)
+        var = torch.empty(n, dtype=torch.float64, device=self.dev)
+        K = T = None
+        for lo in range(0, n, chunk):
             xc = xs[lo:lo + chunk].contiguous()
-            fz, fx, _ = self._field_forward(xc)
-            if zz is None:
-                zz = self._zz_forward(fz, s)
-            K, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"])
-            _, q = o.rowquad(K, zz["C"])
-            means.append(mu)
-            variances.append((s + self.jitter_xx + q).clamp_min(1e-6))
-        return torch.cat(means), torch.cat(variances)
+            fx = self._field_apply(xc, fc)
+            if K is None or K.shape[0] != xc.shape[0]:
+                K = torch.empty(xc.shape[0], self.M, dtype=torch.float64, device=self.dev)
+                T = torch.empty_like(K)
+            _, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"], out=K)
+            _, q = o.rowquad(K, zz["C"], T=T)
+            mean[lo:lo + chunk] = mu
+            var[lo:lo + chunk] = (s + self.jitter_xx + q).clamp_min(1e-6)
+        return mean, var
