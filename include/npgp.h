@@ -89,6 +89,10 @@ int npgp_rowquad(int n, int M, const double* K, long ldk, const double* C, long 
  * Phi = Kzx Kxz (models/gibbs_kernels.py:222-225). */
 int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const double* w, double* Out, long ldo,
                npgp_stream_t stream);
+/* Same with a device-side hint: if *uniform_count == uniform_target all weights equal w[0] and the unweighted inner
+ * loop is taken (SVGP-Gibbs: w = g_v is constant unless a variance was clamped; npgp_gauss_ell counts unclamped rows). */
+int npgp_wsyrk_hint(int n, int M, double alpha, const double* K, long ldk, const double* w, const double* uniform_count,
+                    double uniform_target, double* Out, long ldo, npgp_stream_t stream);
 int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t stream);
 /* measurement switch for the GEMM family: 0 = 128x128 tiles (1 CTA/SM), 1 = 128x64 tiles (2 CTAs/SM, default) */
 int npgp_set_gemm_config(int cfg);

@@ -55,6 +55,43 @@ __device__ __forceinline__ void st_v2(double* p, double a, double b) {
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Row-side reduction of the pairwise backward kernels.  Every lane holds NRC partial sums for the current row (over its
+// own columns); the warp needs their sums over the 32 lanes.  A shuffle tree costs 5*NRC add+shuffle steps per row.
+// Instead each lane parks its partials in a warp-private, padded shared-memory panel and every RB = 32/NRC rows one
+// lane per (row, component) adds up the 32 entries of a panel line (conflict free: line length 33): about
+// 32/RB adds per row instead of 5*NRC.
+template <int NRC>
+struct RowReducer {
+  static constexpr int RB = (32 / NRC) > 0 ? (32 / NRC) : 1;   // rows per batch
+  static constexpr int LINES = RB * NRC;
+  static constexpr int PANEL = LINES * 33;                      // doubles per warp
+  double* panel;  // this warp's panel
+  int lane;
+  __device__ __forceinline__ RowReducer(double* smem_base, int warp, int lane_) : panel(smem_base + warp * PANEL), lane(lane_) {}
+  __device__ __forceinline__ void put(int r, int comp, double v) { panel[((r % RB) * NRC + comp) * 33 + lane]  = v; }
+  // call after the puts of row r; `out(row, comp, sum)` is invoked by one lane per finished (row, comp)
+  template <class F>
+  __device__ __forceinline__ void flush_if_due(int r, int nr, F out) {
+    const int slot = r % RB;
+    if (slot != RB - 1 && r != nr - 1) return;
+    __syncwarp();
+    const int nvals = (slot + 1) * NRC;
+    for (int v = lane; v < nvals; v += 32) {
+      const double* line = panel + v * 33;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 32; k += 4) {
+        a0 += line[k];
+        a1 += line[k + 1];
+        a2 += line[k + 2];
+        a3 += line[k + 3];
+      }
+      out(r - slot + v / NRC, v % NRC, (a0 + a1) + (a2 + a3));
+    }
+    __syncwarp();
+  }
+};
+
 // ---- tiling shared by the pairwise (Gibbs / RBF) tile kernels ----
 constexpr int kNT = 128;         // threads per CTA
 constexpr int kCPT = 2;          // columns per thread (16-byte stores)

@@ -49,6 +49,8 @@ struct GemmParams {
   int out_tri;       // 0 all tiles, 1 only tiles touching the lower triangle, 2 only the upper
   int splits;        // split-K factor (gridDim.z); > 1 => atomicAdd epilogue, C must be pre-scaled by the caller
   const double* w;   // optional weights along K (scales op(A)[m][k] by w[k])
+  const double* w_uniform_count;  // optional device scalar: if *w_uniform_count == w_uniform_target every weight equals
+  double w_uniform_target;        //   w[0], so the kernel skips the per-fragment multiplies and scales the epilogue
   const double* dotK;  // optional: q[row] += sum_col acc[row][col] * dotK[row][col]
   long lddot;
   double* q;
@@ -149,6 +151,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
+  // weights known (on the device) to be all equal: fold them into the epilogue
+  const bool w_uniform = HAS_W && p.w_uniform_count && (*p.w_uniform_count == p.w_uniform_target);
+  const double alpha_eff = w_uniform ? p.alpha * p.w[0] : p.alpha;
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
       la.load_edge(sA, kb + idx * BK, ke);
       lb.load_edge(sB, kb + idx * BK, ke);
     }
-    if (HAS_W) {
+    if (HAS_W && !w_uniform) {
       double* sW = sB + LB::TILE;
       const int k = kb + idx * BK + tid;
       if (tid < BK) sW[tid] = (k < ke) ? p.w[k] : 0.0;
@@ -205,7 +210,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
         const int m = wm0 + mt * 8 + g;
         a[mt] = A_KCONTIG ? sA[m * LA::LDS_K + kk + t4] : sA[(kk + t4) * LA::LDMN + m];
       }
-      if (HAS_W) {
+      if (HAS_W && !w_uniform) {
         const double wk = sW[kk + t4];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) a[mt] *= wk;
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
       const int col = n0 + wn0 + nt * 8 + 2 * t4;
       if (row < p.M && col < p.N) {
         const bool two = (col + 1 < p.N);
-        double v0 = p.alpha * acc[mt][nt][0], v1 = p.alpha * acc[mt][nt][1];
+        double v0 = alpha_eff * acc[mt][nt][0], v1 = alpha_eff * acc[mt][nt][1];
         double* cp = p.C + (long)row * p.ldc + col;
         if (p.splits > 1) {
           atomicAdd(cp, v0);
@@ -390,8 +395,26 @@ extern "C" int npgp_rowquad(int n, int M, const double* K, long ldk, const doubl
 }
 
 // Out (M x M, symmetric) = alpha * K^T diag(w) K, K is (n x M); w may be NULL.  Out is overwritten.
+static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, const double* w,
+                      const double* w_uniform_count, double w_uniform_target, double* Out, long ldo, cudaStream_t stream);
+
 extern "C" int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const double* w, double* Out, long ldo,
                           cudaStream_t stream) {
+  return wsyrk_impl(n, M, alpha, K, ldk, w, nullptr, 0.0, Out, ldo, stream);
+}
+
+// Same, with a device-side hint: when *uniform_count == uniform_target all weights are equal (to w[0]) and the kernel
+// takes the unweighted inner loop.  (SVGP-Gibbs: w = g_v is constant unless a predictive variance was clamped;
+// npgp_gauss_ell counts the unclamped rows.)
+extern "C" int npgp_wsyrk_hint(int n, int M, double alpha, const double* K, long ldk, const double* w,
+                               const double* uniform_count, double uniform_target, double* Out, long ldo,
+                               cudaStream_t stream) {
+  return wsyrk_impl(n, M, alpha, K, ldk, w, uniform_count, uniform_target, Out, ldo, stream);
+}
+
+static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, const double* w,
+                      const double* w_uniform_count, double w_uniform_target, double* Out, long ldo,
+                      cudaStream_t stream) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
   if (!Out || (n > 0 && !K)) return NPGP_EINVAL;
@@ -399,6 +422,7 @@ extern "C" int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk,
   GemmParams p{};
   p.M = M; p.N = M; p.K = n; p.A = K; p.lda = ldk; p.B = K; p.ldb = ldk; p.C = Out; p.ldc = ldo;
   p.alpha = alpha; p.beta = 0.0; p.out_tri = 2; p.w = w;
+  p.w_uniform_count = w ? w_uniform_count : nullptr; p.w_uniform_target = w_uniform_target;
   const long tiles = ((long)ceil_div(M, tile_bm()) * ceil_div(M, tile_bn()) + ceil_div(M, tile_bm())) / 2;
   int s = (int)max(1L, (long)(kNumSMs * ctas_per_sm()) / tiles);
   s = min(s, max(1, n / (16 * kMaxBK)));

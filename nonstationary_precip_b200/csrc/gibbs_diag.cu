@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
   __shared__ double sx[kTI][D], sa[kTI][D], sl[kTI][D], sc[kTI], srs[kTI], srv[kTI];
   __shared__ double part[NW][kTI][NRC];
   __shared__ double red[32];
+  __shared__ double panels[NW * RowReducer<NRC>::PANEL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RowReducer<NRC> rr(panels, warp, lane);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -187,23 +189,15 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
           }
         }
       }
-      // row-side: reduce over the warp's 64 columns, one partial per warp
+      // row-side: reduce over the warp's 64 columns (batched shared-memory reduction), one partial per warp
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const double v = warp_sum(rw[d]);
-        if (lane == 0) part[warp][r][d] = v;
-      }
-      {
-        const double v = warp_sum(rs0);
-        if (lane == 0) part[warp][r][D] = v;
-      }
+      for (int d = 0; d < D; ++d) rr.put(r, d, rw[d]);
+      rr.put(r, D, rs0);
       if (DX1) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const double v = warp_sum(rxz[d]);
-          if (lane == 0) part[warp][r][D + 1 + d] = v;
-        }
+        for (int d = 0; d < D; ++d) rr.put(r, D + 1 + d, rxz[d]);
       }
+      rr.flush_if_due(r, nr, [&](int row, int comp, double v) { part[warp][row][comp] = v; });
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nr * NRC; t += kNT) {

@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
   __shared__ double sx[kTI][d], sS[kTI][P], sq[kTI], srs[kTI], srv[kTI];
   __shared__ double part[NW][kTI][NRC];
   __shared__ double red[32];
+  __shared__ double panels[NW * RowReducer<NRC>::PANEL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RowReducer<NRC> rr(panels, warp, lane);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -205,21 +207,13 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
         }
       }
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const double v = warp_sum(rW[p]);
-        if (lane == 0) part[warp][r][p] = v;
-      }
-      {
-        const double v = warp_sum(rs0);
-        if (lane == 0) part[warp][r][P] = v;
-      }
+      for (int p = 0; p < P; ++p) rr.put(r, p, rW[p]);
+      rr.put(r, P, rs0);
       if (DX1) {
 #pragma unroll
-        for (int k = 0; k < d; ++k) {
-          const double v = warp_sum(rxz[k]);
-          if (lane == 0) part[warp][r][P + 1 + k] = v;
-        }
+        for (int k = 0; k < d; ++k) rr.put(r, P + 1 + k, rxz[k]);
       }
+      rr.flush_if_due(r, nr, [&](int row, int comp, double v) { part[warp][row][comp] = v; });
     }
     __syncthreads();
     for (int t = threadIdx.x; t < nr * NRC; t += kNT) {

@@ -164,13 +164,18 @@ def rowquad(K, Cm, need_q=True, T=None):
     return T, q
 
 
-def wsyrk(K, w=None, alpha=1.0, out=None):
-    """alpha * K^T diag(w) K (symmetric M x M)."""
+def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0):
+    """alpha * K^T diag(w) K (symmetric M x M).  uniform_count (device scalar) == uniform_target tells the kernel, on
+    the device, that all weights are equal."""
     n, M = K.shape
     if out is None:
         out = torch.empty(M, M, dtype=torch.float64, device=K.device)
-    check(lib().npgp_wsyrk(n, M, float(alpha), ptr(K), K.stride(0), ptr(_c(w)), ptr(out), out.stride(0), stream()),
-          "npgp_wsyrk")
+    if uniform_count is not None and w is not None:
+        check(lib().npgp_wsyrk_hint(n, M, float(alpha), ptr(K), K.stride(0), ptr(_c(w)), ptr(uniform_count),
+                                    float(uniform_target), ptr(out), out.stride(0), stream()), "npgp_wsyrk_hint")
+    else:
+        check(lib().npgp_wsyrk(n, M, float(alpha), ptr(K), K.stride(0), ptr(_c(w)), ptr(out), out.stride(0), stream()),
+              "npgp_wsyrk")
     return out
 
 

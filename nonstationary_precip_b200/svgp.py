@@ -294,7 +294,8 @@ class SVGPGibbs:
             with self._sec("colwsum"):
                 du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
-                dC = o.wsyrk(K, w=gv)
+                # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
+                dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
             if wsyrk_done is not None:
                 wsyrk_done.record()
             with self._sec("m3_bwd+kzz_bwd"):

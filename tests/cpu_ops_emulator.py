@@ -138,7 +138,7 @@ def rowquad(K, Cm, need_q=True, T=None):
     return Tn, ((Tn * K).sum(-1) if need_q else None)
 
 
-def wsyrk(K, w=None, alpha=1.0, out=None):
+def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0):
     R = alpha * (K.T @ (K if w is None else w[:, None] * K))
     if out is not None:
         out.copy_(R)

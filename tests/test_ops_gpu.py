@@ -215,3 +215,20 @@ def test_potrf_reports_first_bad_pivot(ops):
     A[130, 130] = -1.0
     _, _, info = ops.potrf_inv(A)
     assert int(info) == 131
+
+
+def test_wsyrk_uniform_weight_hint(ops):
+    """Device-side hint: equal weights -> unweighted inner loop with the weight folded into the epilogue; if the hint
+    does not hold the weights are applied per fragment."""
+    g = torch.Generator().manual_seed(12)
+    n, M = 1500, 192
+    K = torch.randn(n, M, generator=g).cuda()
+    w_const = torch.full((n,), -0.37, device="cuda")
+    count = torch.tensor([float(n)], device="cuda")
+    want = K.T @ (w_const[:, None] * K)
+    assert rel(ops.wsyrk(K, w_const, uniform_count=count, uniform_target=float(n)), want) < 1e-12
+    w_var = w_const.clone()
+    w_var[::7] = 0.0  # e.g. clamped variances
+    count2 = torch.tensor([float((w_var != 0).sum())], device="cuda")
+    want2 = K.T @ (w_var[:, None] * K)
+    assert rel(ops.wsyrk(K, w_var, uniform_count=count2, uniform_target=float(n)), want2) < 1e-12
