@@ -94,7 +94,8 @@ int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const doub
 int npgp_wsyrk_hint(int n, int M, double alpha, const double* K, long ldk, const double* w, const double* uniform_count,
                     double uniform_target, double* Out, long ldo, npgp_stream_t stream);
 int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t stream);
-/* measurement switch for the GEMM family: 0 = 128x128 tiles (1 CTA/SM), 1 = 128x64 tiles (2 CTAs/SM, default) */
+/* measurement switch for the GEMM family: 0 = 128x128 tiles (1 CTA/SM), 1/2 = 128x64 (2 CTAs/SM), 3/4 = 64x64 tiles with
+ * 4-warp CTAs (3/4 CTAs/SM), 5 = auto (default) */
 int npgp_set_gemm_config(int cfg);
 
 /* ---- (c) blocked Cholesky + inverse factor --------------------------------------------------------------------------

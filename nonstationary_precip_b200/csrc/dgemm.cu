@@ -7,10 +7,10 @@
 // These replace the cuBLAS/MAGMA calls GPyTorch issues for  A = L^-1 Kzx,  A^T (S - I) A  and  Kzx Kxz
 // (reference models/gibbs_kernels.py:222-232 via LowRankRootLazyTensor; models/dgps.py:25-35 via VariationalStrategy).
 //
-// Tiling (templated): BK = 16, 3-stage cp.async pipeline, 8 warps per CTA.  Default "dual" configuration: 128x64 CTA
-// tile, 32x32 warp tiles (32 accumulator doubles per thread) so that TWO CTAs = 16 warps are resident per SM and one
-// CTA's barrier / address phase is covered by the other's DMMA stream; "big" configuration: 128x128 tile, 64x32 warp
-// tiles, one CTA per SM.  Shared-memory tiles are stored either K-contiguous [rows][16+4] or MN-contiguous
+// Tiling (templated, measured on B200, see profiles/): BK = 16, 3-stage cp.async pipeline, 32x32 warp tiles (32
+// accumulator doubles per thread).  Default: 64x64 CTA tile, 4 warps per CTA, 3-4 CTAs resident per SM, so that one CTA's
+// barrier / producer phase is covered by the others' DMMA streams (34.3 TF/s = 93 % of the DMMA peak at C2; the
+// 128x64 / 8-warp / 2-CTA variant reaches 32.2, the 128x128 / 1-CTA variant 29.9; cuBLAS 35.2).  Shared-memory tiles are stored either K-contiguous [rows][16+4] or MN-contiguous
 // [16][cols+4], whichever matches the operand's global layout; with a leading dimension = 4 (mod 16) doubles both
 // fragment-load patterns are bank-conflict free for 64-bit accesses.  Chunk addresses are computed once per CTA; the
 // per-stage producer work is a pointer bump (plus a byte count at ragged edges).
@@ -18,7 +18,6 @@
 
 namespace npgp {
 
-constexpr int GEMM_THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -59,7 +58,7 @@ struct GemmParams {
 // One operand tile of TR "rows" (the M or N extent) x BK, loaded with 16-byte cp.async.  A thread owns PASSES chunks
 // that differ by a uniform stride, so the steady-state producer work per stage is PASSES cp.async + one pointer bump;
 // only edge tiles and the ragged last k-step take the predicated path.
-template <int TR, int BK, bool KCONTIG>
+template <int TR, int BK, bool KCONTIG, int GEMM_THREADS>
 struct TileLoader {
   static constexpr int LDS_K = BK + 4;                      // K-contiguous tile: [TR][BK+4], = 4 (mod 16)
   static constexpr int LDMN = TR + 4;                       // MN-contiguous tile: [BK][TR+4], = 4 (mod 16)
@@ -117,10 +116,11 @@ struct TileLoader {
   }
 };
 
-template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool A_KCONTIG, bool B_KCONTIG, bool HAS_W, int MINB>
+template <int BM, int BN, int WM, int WN, int BK, int STAGES, bool A_KCONTIG, bool B_KCONTIG, bool HAS_W, int MINB,
+          int GEMM_THREADS>
 __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p) {
-  using LA = TileLoader<BM, BK, A_KCONTIG>;
-  using LB = TileLoader<BN, BK, B_KCONTIG>;
+  using LA = TileLoader<BM, BK, A_KCONTIG, GEMM_THREADS>;
+  using LB = TileLoader<BN, BK, B_KCONTIG, GEMM_THREADS>;
   constexpr int STAGE_DOUBLES = LA::TILE + LB::TILE + BK;
   constexpr int MT = WM / 8, NT = WN / 8;
   constexpr int WARPS_N = BN / WN;
@@ -271,15 +271,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
 }
 
 // tile configurations (switchable at run time for A/B measurements, see npgp_set_gemm_config)
-struct Cfg0 { static constexpr int BM = 128, BN = 128, WM = 64, WN = 32, BK = 16, ST = 3, MINB = 1; };  // 1 CTA/SM
-struct Cfg1 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 16, ST = 3, MINB = 2; };   // 2 CTAs/SM
-struct Cfg2 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 32, ST = 2, MINB = 2; };
-struct Cfg3 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 16, ST = 4, MINB = 2; };
-struct Cfg4 { static constexpr int BM = 128, BN = 128, WM = 64, WN = 32, BK = 32, ST = 2, MINB = 1; };
+struct Cfg0 { static constexpr int BM = 128, BN = 128, WM = 64, WN = 32, BK = 16, ST = 3, MINB = 1, NT = 256; };  // 1 CTA/SM
+struct Cfg1 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 16, ST = 3, MINB = 2, NT = 256; };   // 2 CTAs/SM
+struct Cfg2 { static constexpr int BM = 128, BN = 64, WM = 32, WN = 32, BK = 32, ST = 2, MINB = 2, NT = 256; };
+struct Cfg3 { static constexpr int BM = 64, BN = 64, WM = 32, WN = 32, BK = 16, ST = 3, MINB = 3, NT = 128; };     // 3 CTAs/SM
+struct Cfg4 { static constexpr int BM = 64, BN = 64, WM = 32, WN = 32, BK = 16, ST = 3, MINB = 4, NT = 128; };     // 4 CTAs/SM
 
 template <class Cfg, bool AK, bool BK_>
 constexpr int gemm_smem_bytes() {
-  return Cfg::ST * (TileLoader<Cfg::BM, Cfg::BK, AK>::TILE + TileLoader<Cfg::BN, Cfg::BK, BK_>::TILE + Cfg::BK) * 8;
+  return Cfg::ST * (TileLoader<Cfg::BM, Cfg::BK, AK, Cfg::NT>::TILE + TileLoader<Cfg::BN, Cfg::BK, BK_, Cfg::NT>::TILE +
+                    Cfg::BK) * 8;
 }
 
 __global__ void scale_matrix_kernel(int M, int N, double* C, long ldc, double beta, int out_tri) {
@@ -303,8 +304,9 @@ __global__ void symmetrize_kernel(int M, double* C, long ldc, int from_upper) {
 template <class Cfg, bool AK, bool BK_>
 static int launch_cfg(const GemmParams& p, cudaStream_t st) {
   constexpr int smem = gemm_smem_bytes<Cfg, AK, BK_>();
-  auto kern = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, false, Cfg::MINB>;
-  auto kern_w = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, true, Cfg::MINB>;
+  constexpr int GEMM_THREADS = Cfg::NT;
+  auto kern = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, false, Cfg::MINB, Cfg::NT>;
+  auto kern_w = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, true, Cfg::MINB, Cfg::NT>;
   static bool attr_set = false;
   if (!attr_set) {
     NPGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -318,7 +320,7 @@ static int launch_cfg(const GemmParams& p, cudaStream_t st) {
   return NPGP_OK;
 }
 
-static int g_gemm_cfg = 1;
+static int g_gemm_cfg = 5;  // 5 = auto: 64x64 tiles, 4 CTAs/SM for tall problems, 3 CTAs/SM for M x M ones
 
 template <class Cfg>
 static int launch_layout(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t st) {
@@ -330,17 +332,21 @@ static int launch_layout(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t
 
 static int launch_gemm(bool a_kc, bool b_kc, const GemmParams& p, cudaStream_t st) {
   switch (g_gemm_cfg) {
+    case 5:
+      if ((long)p.M * p.N > (4096L * 4096L) || p.K > 8192) return launch_layout<Cfg4>(a_kc, b_kc, p, st);
+      return launch_layout<Cfg3>(a_kc, b_kc, p, st);
     case 0: return launch_layout<Cfg0>(a_kc, b_kc, p, st);
     case 2: return launch_layout<Cfg2>(a_kc, b_kc, p, st);
     case 3: return launch_layout<Cfg3>(a_kc, b_kc, p, st);
     case 4: return launch_layout<Cfg4>(a_kc, b_kc, p, st);
-    default: return launch_layout<Cfg1>(a_kc, b_kc, p, st);
+    case 1: return launch_layout<Cfg1>(a_kc, b_kc, p, st);
+    default: return launch_layout<Cfg4>(a_kc, b_kc, p, st);
   }
 }
 
-static int tile_bm() { return 128; }
-static int tile_bn() { return (g_gemm_cfg == 0 || g_gemm_cfg == 4) ? 128 : 64; }
-static int ctas_per_sm() { return (g_gemm_cfg == 0 || g_gemm_cfg == 4) ? 1 : 2; }
+static int tile_bm() { return (g_gemm_cfg >= 3) ? 64 : 128; }
+static int tile_bn() { return (g_gemm_cfg == 0) ? 128 : 64; }
+static int ctas_per_sm() { return g_gemm_cfg == 0 ? 1 : (g_gemm_cfg >= 4 ? 4 : (g_gemm_cfg == 3 ? 3 : 2)); }
 constexpr int kMaxBK = 32;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -450,7 +456,7 @@ extern "C" int npgp_symmetrize(int M, double* C, long ldc, int from_upper, cudaS
 
 // measurement switch: 0 = 128x128 tiles (1 CTA/SM), 1 = 128x64 tiles (2 CTAs/SM, default)
 extern "C" int npgp_set_gemm_config(int cfg) {
-  if (cfg < 0 || cfg > 4) return NPGP_EINVAL;
+  if (cfg < 0 || cfg > 5) return NPGP_EINVAL;
   npgp::g_gemm_cfg = cfg;
   return NPGP_OK;
 }

@@ -94,7 +94,7 @@ def main():
     T = torch.empty(B, M, **f64)
     Out = torch.empty(M, M, **f64)
     A1, A2 = torch.randn(M, M, **f64), torch.randn(M, M, **f64)
-    for cfg, nm in ((0, "128x128,bk16,s3"), (1, "128x64,bk16,s3"), (2, "128x64,bk32,s2"), (3, "128x64,bk16,s4"), (4, "128x128,bk32,s2")):
+    for cfg, nm in ((0, "128x128,bk16,s3"), (1, "128x64,bk16,s3"), (2, "128x64,bk32,s2"), (3, "64x64,128thr,3cta"), (4, "64x64,128thr,4cta")):
         check(lib().npgp_set_gemm_config(cfg), "cfg")
         ms, best = timeit(lambda: ops.rowquad(K, Cm, T=T))
         report("rowquad[%s]" % nm, ms, best, tflops=round(2 * B * M * M / best / 1e9, 2))
@@ -103,7 +103,7 @@ def main():
                tflops_useful=round(B * M * (M + 128) / best / 1e9, 2))
         ms, best = timeit(lambda: ops.dgemm(A1, A2, C=Out))
         report("dgemm_MMM[%s]" % nm, ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
-    check(lib().npgp_set_gemm_config(1), "cfg")
+    check(lib().npgp_set_gemm_config(5), "cfg")
     ms, best = timeit(lambda: torch.matmul(A1, A2, out=Out))
     report("cublas_dgemm_MMM(reference point)", ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
     ms, best = timeit(lambda: torch.matmul(K, Cm, out=T), iters=5)
