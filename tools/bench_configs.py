@@ -89,6 +89,35 @@ def c4():
         "loss": loss, "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
 
 
+def c3():
+    """Spatial (Gibbs) part of config 3 at full scale: streamed SGPR objective + gradients, N = 4 194 304 rows shaped like
+    uib_spatio_temporal.csv (1024 time steps x 64x64 cells; here the lon/lat columns, z-scored), M = 2048."""
+    from nonstationary_precip_b200.sgpr import SGPRGibbsStream
+    N = int(os.environ.get("N", 1 << 22))
+    M = int(os.environ.get("M", 2048))
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    g = torch.Generator().manual_seed(3)
+    cells = torch.stack(torch.meshgrid(torch.arange(64, dtype=torch.float64), torch.arange(64, dtype=torch.float64),
+                                       indexing="ij"), -1).reshape(-1, 2)
+    cells = (cells - cells.mean(0)) / cells.std(0)
+    idx = torch.arange(N) % 4096
+    x = (cells[idx] + 0.01 * torch.randn(N, 2, generator=g, dtype=torch.float64)).cuda()
+    y = (torch.exp(-(x ** 2).sum(-1)) * torch.sin(2 * math.pi * torch.arange(N, device="cuda") / (4096.0 * 12.0))).contiguous()
+    Z = x[torch.randperm(N, generator=g)[:M].cuda()].clone()
+    D = 2
+    model = SGPRGibbsStream(Z, torch.full((D, M), math.log(0.3), **f64), torch.full((D,), math.log(0.3), **f64),
+                            torch.ones(D, **f64), torch.full((D, D), 1.3, **f64), outputscale=0.644, noise=0.05)
+    n_loc = N // world
+    xs, ys = x[rank * n_loc:(rank + 1) * n_loc], y[rank * n_loc:(rank + 1) * n_loc]
+    best, med = ev_time(lambda: model.neg_objective_and_grad(xs, ys, chunk=65536, n_total=N), iters=2, warm=1)
+    loss = model.neg_objective_and_grad(xs, ys, chunk=65536, n_total=N).item()
+    flop = 3.0 * n_loc * M * M  # SYRK (N M^2) + second-pass GEMM (2 N M^2)
+    print(json.dumps({"config": "c3 (spatial Gibbs part) streamed SGPR objective+grad, N=%d, M=%d, rows on this rank %d" % (
+        N, M, n_loc), "ms_per_eval": best, "evals_per_s": 1e3 / best, "tflops_3NM2": flop / best / 1e9, "loss": loss,
+        "finite_grads": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
+        "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+
+
 def c1():
     from nonstationary_precip_b200.gp_base import ExactMarginalLogLikelihood, GaussianLikelihood
     from nonstationary_precip_b200.models.gibbs_kernels import LogNormalPriorProcess
