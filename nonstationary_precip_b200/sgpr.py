@@ -3,9 +3,9 @@
 evaluated WITHOUT materialising the N x M root, so that it runs at the scale of BASELINE config 3 (N = 4M rows,
 M = 2048), where the reference's `k_ux1.matmul(inv_root)` would need 68 GB.
 
-With K = Gibbs(X, Z) (unscaled, rows streamed in chunks), Kzz = L L^T, P = L^-1, R = K P^T:
-    R^T R = P (K^T K) P^T,   R^T y = P (K^T y),   tr(R R^T) = tr(P K^T K P^T)
-so one pass over the rows accumulates only  A = K^T K (M x M, DMMA SYRK),  b = K^T y  and  y^T y.  Everything else is
+With K = Gibbs(X, Z) (unscaled, rows streamed in chunks) the bound depends on the rows only through
+    A = K^T K (M x M, DMMA SYRK),   b = K^T y,   y^T y
+(the root R = K U^-1 of the reference satisfies R^T R = U^-T A U^-1), so one pass over the rows accumulates just those.  Everything else is
 M x M algebra on the blocked Cholesky / GEMM kernels (differentiated by the autograd Functions of `functional.py`).
 The data-side gradient needs a second pass:  dObj/dK_chunk = K_chunk (dA + dA^T) + y_chunk db^T, formed by one DMMA GEMM
 per chunk and consumed inside the analytic Gibbs backward kernel (never stored as a gradient matrix); the lengthscale
@@ -33,8 +33,9 @@ def _inv_softplus(v: float) -> float:
 
 class SGPRGibbsStream(torch.nn.Module):
     def __init__(self, Z, log_ell_z, prior_c, prior_os, prior_lam, outputscale=0.644, noise=0.011,
-                 learn_inducing_locations=True, include_prior=True):
+                 learn_inducing_locations=True, include_prior=True, jitter_zz=0.0):
         super().__init__()
+        self.jitter_zz = jitter_zz
         self.Z = torch.nn.Parameter(Z.clone(), requires_grad=learn_inducing_locations)
         self.log_ell_z = torch.nn.Parameter(log_ell_z.clone())
         self.raw_outputscale = torch.nn.Parameter(torch.tensor([_inv_softplus(outputscale)], dtype=torch.float64,
@@ -63,8 +64,15 @@ class SGPRGibbsStream(torch.nn.Module):
                 lp = lp + (-0.5 * (r * a).sum() - torch.log(torch.diagonal(Lb)).sum() - 0.5 * M * LOG2PI) / M
         alpha = torch.stack(alphas)
         Kzz = F.gibbs_diag(self.Z, ell_z, self.Z, ell_z)
-        L, P = F.psd_safe_chol_inv(Kzz)
-        return ell_z, alpha, P, lp
+        # psd_safe_cholesky ladder (gibbs_kernels.py:201), keeping the jittered matrix: it is reused in Sigma below
+        for jit in (0.0, 1e-8, 1e-7, 1e-6):
+            Kj = Kzz + (self.jitter_zz + jit) * eye
+            L, P, info = F.chol_inv(Kj)
+            if int(info) == 0:
+                break
+        else:
+            raise RuntimeError("Kzz not positive definite after adding jitter up to 1e-6")
+        return ell_z, alpha, (Kj, L, P), lp
 
     def _chunk_forward(self, xc, ell_z, alpha, K_out=None):
         ell_x = ops.rbf_matvec_fwd(xc, self.Z.detach(), self.prior_lam, self.prior_os, alpha.unsqueeze(-1),
@@ -81,7 +89,7 @@ class SGPRGibbsStream(torch.nn.Module):
         n_loc = x.shape[0]
         n = n_total if n_total is not None else n_loc
         M, D = self.Z.shape
-        ell_z, alpha, P, lp = self._z_side()
+        ell_z, alpha, (Kzz, L, P), lp = self._z_side()
         ell_zd, alphad = ell_z.detach().contiguous(), alpha.detach().contiguous()
 
         # ---- pass 1: A = K^T K, b = K^T y, y^T y
@@ -106,15 +114,17 @@ class SGPRGibbsStream(torch.nn.Module):
         # ---- M x M algebra (autograd over the Cholesky / GEMM kernels)
         s = _softplus(self.raw_outputscale).reshape(())
         noise = (1e-4 + _softplus(self.raw_noise)).reshape(())
-        Phi = F.matmul(F.matmul(P, A), P.T)
-        c = F.matmul(P, b)
-        Bm = torch.eye(M, dtype=torch.float64, device=dev) + (s / noise) * Phi
-        LB, PB = F.psd_safe_chol_inv(0.5 * (Bm + Bm.T))
-        w = F.matmul(PB, c)
+        # Numerically stable form: with Sigma = Kzz + (s/noise) A (positive definite by construction),
+        #   log det(s Q + noise I) = n log noise + log det Sigma - log det Kzz,
+        #   y^T (s Q + noise I)^-1 y = y^T y / noise - (s / noise^2) b^T Sigma^-1 b,     Q = K Kzz^-1 K^T.
+        # (Forming I + (s/noise) P A P^T instead loses positive definiteness for ill-conditioned Kzz.)
+        Sigma = Kzz + (s / noise) * (0.5 * (A + A.T))
+        LS, PS = F.psd_safe_chol_inv(Sigma)
+        w = F.matmul(PS, b)
         quad = yy / noise - (s / (noise * noise)) * (w * w).sum()
-        logdet = 2.0 * torch.log(torch.diagonal(LB)).sum() + n * torch.log(noise)
+        logdet = 2.0 * (torch.log(torch.diagonal(LS)).sum() - torch.log(torch.diagonal(L)).sum()) + n * torch.log(noise)
         ll = -0.5 * (quad + logdet + n * LOG2PI)
-        trace = -0.5 * (n - torch.diagonal(Phi).sum()) / noise
+        trace = -0.5 * (n - (F.matmul(P, A) * P).sum()) / noise  # tr(Kzz^-1 A) = tr(P A P^T)
         obj = (ll + trace + lp) / n
         loss = -obj
         dA, db = torch.autograd.grad(loss, [A, b], retain_graph=True)
