@@ -325,7 +325,10 @@ def run_ours(args):
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},
             "roofline": {"bound": "tensor", "kernel": "dgemm_kernel (rowquad T = K C, FP64 DMMA)", "achieved": rq_tf,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": rq_tf / peak_tf, "traffic": None,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": rq_tf / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at Bl = 65536 from the ncu --set full
+                         # capture in profiles/r01_ncu_rowquad_full_summary.txt (algorithmic: 1082 MB)
+                         "traffic": 1.0542e9 if world == 1 else None,
                          "peak_source": "in-run DMMA.8x8x4 probe; MEASURED_PEAKS.json has no FP64 entry "
                                         "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)"},
             "roofline_kxz": {"bound": "hbm", "kernel": "gibbs_%s fwd+bwd (K written, T read: 16 B/pair)" % args.variant,

@@ -40,7 +40,8 @@ def test_streamed_sgpr_matches_dense_oracle(n, M, D, chunk):
 
 
 def test_streamed_sgpr_rank_sharding_by_emulated_all_reduce():
-    """Two 'ranks' each stream half of the rows; with the sums exchanged the objective equals the single-rank one."""
+    """Two 'ranks' each stream half of the rows.  The all-reduce is emulated on one GPU by running each rank's passes and
+    exchanging the packed partial sums by hand; the result must equal the single-rank objective and gradients."""
     from nonstationary_precip_b200.sgpr import SGPRGibbsStream
     g = torch.Generator().manual_seed(3)
     n, M, D = 600, 40, 2
@@ -49,48 +50,37 @@ def test_streamed_sgpr_rank_sharding_by_emulated_all_reduce():
     Z = x[:M].clone()
     le = torch.full((D, M), math.log(0.3)).cuda()
     c, os_, lam = torch.full((D,), math.log(0.3)).cuda(), torch.ones(D).cuda(), torch.full((D, D), 1.3).cuda()
-    full = SGPRGibbsStream(Z, le, c, os_, lam)
+    halves = [(x[:n // 2], y[:n // 2]), (x[n // 2:], y[n // 2:])]
+    new = lambda: SGPRGibbsStream(Z, le, c, os_, lam)  # noqa: E731
+    full = new()
     l_full = full.neg_objective_and_grad(x, y, chunk=128)
-    # emulate the all-reduce: rank 1's partial sums are precomputed and added to rank 0's
-    r1 = SGPRGibbsStream(Z, le, c, os_, lam)
-    stash = []
-    r1.neg_objective_and_grad(x[n // 2:], y[n // 2:], chunk=128, n_total=n, all_reduce=lambda t: stash.append(t.clone()))
-    it = iter(stash)
-    r0 = SGPRGibbsStream(Z, le, c, os_, lam)
 
-    def fake_all_reduce(t):
-        other = next(it)
-        t += other
+    # round 1: every rank's first-pass sums (A, b, y^T y)
+    first = []
+    for xs, ys in halves:
+        got = []
+        new().neg_objective_and_grad(xs, ys, chunk=128, n_total=n, all_reduce=lambda t, got=got: got.append(t.clone()))
+        first.append(got[0])
+    tot1 = first[0] + first[1]
 
-    # rank 1's second-pass sums depend on dA/db from the GLOBAL objective, so recompute them with rank 0's sums first
-    stash0 = []
-    r0.neg_objective_and_grad(x[:n // 2], y[:n // 2], chunk=128, n_total=n, all_reduce=lambda t: stash0.append(t.clone()))
-    tot1 = stash[0] + stash0[0]
+    # round 2: with the global first-pass sums, every rank's second-pass sums (data-side gradients)
+    def reducer(second_of_other=None, capture=None):
+        state = {"k": 0}
 
-    class TwoPass:
-        def __init__(self, other_second=None):
-            self.k, self.other_second = 0, other_second
-
-        def __call__(self, t):
-            if self.k == 0:
+        def ar(t):
+            if state["k"] == 0:
                 t.copy_(tot1)
-            elif self.other_second is not None:
-                t += self.other_second
-            self.k += 1
+            elif second_of_other is not None:
+                t += second_of_other
+            elif capture is not None:
+                capture.append(t.clone())
+            state["k"] += 1
+        return ar
 
     cap = []
-    r1b = SGPRGibbsStream(Z, le, c, os_, lam)
-
-    def ar1(t, st=[0]):
-        if st[0] == 0:
-            t.copy_(tot1)
-        else:
-            cap.append(t.clone())
-        st[0] += 1
-
-    r1b.neg_objective_and_grad(x[n // 2:], y[n // 2:], chunk=128, n_total=n, all_reduce=ar1)
-    r0b = SGPRGibbsStream(Z, le, c, os_, lam)
-    l0 = r0b.neg_objective_and_grad(x[:n // 2], y[:n // 2], chunk=128, n_total=n, all_reduce=TwoPass(cap[0]))
+    new().neg_objective_and_grad(*halves[1], chunk=128, n_total=n, all_reduce=reducer(capture=cap))
+    r0 = new()
+    l0 = r0.neg_objective_and_grad(*halves[0], chunk=128, n_total=n, all_reduce=reducer(second_of_other=cap[0]))
     assert abs(l0.item() - l_full.item()) < 1e-10 * abs(l_full.item())
-    assert rel(r0b.log_ell_z.grad, full.log_ell_z.grad) < 1e-8
-    assert rel(r0b.Z.grad, full.Z.grad) < 1e-8
+    assert rel(r0.log_ell_z.grad, full.log_ell_z.grad) < 1e-8
+    assert rel(r0.Z.grad, full.Z.grad) < 1e-8
