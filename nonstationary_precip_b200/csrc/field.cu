@@ -6,6 +6,7 @@
 // SparseMultivariateGibbsKernel.expectation_conditional_matrix_variate_dist
 // (reference models/sparse_multivariate_gibbs_kernel.py:67-80; NB = 1, NV = d right-hand sides).
 #include "common.cuh"
+#include "pairmath.cuh"
 
 namespace npgp {
 
@@ -26,6 +27,9 @@ __global__ void __launch_bounds__(kFT) rbf_matvec_fwd_kernel(int n, int m, const
   __shared__ double sz[kFS][kFChunk][NB][d];   // pre-scaled column coordinates z/lam_b
   __shared__ double sv[kFS][kFChunk][NB][NV];  // os_b * V
   __shared__ double sacc[kFS][kFR][NB * NV];
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * kFR + lane;
   double il[NB][d], xs[NB][d], acc[NB][NV];
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(kFT) rbf_matvec_fwd_kernel(int n, int m, const
           const double df = xs[b][a] - sz[warp][t][b][a];
           q = fma(df, df, q);
         }
-        const double k = exp(-0.5 * q);
+        const double k = exp_neg(-0.5 * q, sexp);
 #pragma unroll
         for (int c = 0; c < NV; ++c) acc[b][c] = fma(k, sv[warp][t][b][c], acc[b][c]);
       }
@@ -101,6 +105,9 @@ __global__ void __launch_bounds__(kFT) rbf_matvec_bwd_kernel(int n, int m, const
   __shared__ double sxr[kFS][kFChunk][NB][d];   // pre-scaled row coordinates x/lam_b
   __shared__ double sg[kFS][kFChunk][NB][NV];   // os_b * dOut
   __shared__ double sacc[kFS][kFR][NB * NV + d];
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * kFR + lane;
   double il[NB][d], zs[NB][d], vj[NB][NV], aV[NB][NV], az[d];
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(kFT) rbf_matvec_bwd_kernel(int n, int m, const
           df[a] = sxr[warp][t][b][a] - zs[b][a];
           q = fma(df[a], df[a], q);
         }
-        const double k = exp(-0.5 * q);
+        const double k = exp_neg(-0.5 * q, sexp);
         double gv = 0.0;
 #pragma unroll
         for (int c = 0; c < NV; ++c) {

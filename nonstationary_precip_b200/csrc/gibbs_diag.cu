@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_fwd_kernel(int n1, int n2, con
                                                              long ldk, int vec_ok, const double* __restrict__ u,
                                                              double* __restrict__ Ku, int rows_per_cta) {
   __shared__ double sx[kTI][D], sa[kTI][D], sc[kTI];
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -70,8 +72,8 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_fwd_kernel(int n1, int n2, con
     const int nr = min(kTI, row_end - i0);
 #pragma unroll 2
     for (int r = 0; r < nr; ++r) {
-      const double k0 = gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[0], b[0], cj[0]);
-      const double k1 = gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[1], b[1], cj[1]);
+      const double k0 = gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[0], b[0], cj[0], sexp);
+      const double k1 = gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[1], b[1], cj[1], sexp);
       double* krow = K + (long)(i0 + r) * ldk + jbase;
       if (vec_ok && valid[1]) {
         st_v2(krow, k0, k1);
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
   __shared__ double panels[NW * RowReducer<NRC>::PANEL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowReducer<NRC> rr(panels, warp, lane);
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
 #pragma unroll
       for (int c = 0; c < kCPT; ++c) {
         DiagPair<D> p;
-        gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[c], b[c], cj[c], &p);
+        gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[c], b[c], cj[c], sexp, &p);
         const double gk0 = valid[c] ? gv[c] * p.k : 0.0;  // dL/ds contribution (unscaled kernel)
         acc_scale += gk0;
         const double gk = gk0 * s;

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kNT) gibbs_full_fwd_kernel(int n1, int n2, con
                                                              double* __restrict__ Ku, int rows_per_cta) {
   constexpr int P = sym_size(d);
   __shared__ double sx[kTI][d], sS[kTI][P], sq[kTI];
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -87,8 +89,8 @@ __global__ void __launch_bounds__(kNT) gibbs_full_fwd_kernel(int n1, int n2, con
     const int nr = min(kTI, row_end - i0);
 #pragma unroll 2
     for (int r = 0; r < nr; ++r) {
-      const double k0 = gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[0], Sj[0], qj[0], jit2);
-      const double k1 = gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[1], Sj[1], qj[1], jit2);
+      const double k0 = gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[0], Sj[0], qj[0], jit2, sexp);
+      const double k1 = gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[1], Sj[1], qj[1], jit2, sexp);
       double* krow = K + (long)(i0 + r) * ldk + jbase;
       if (vec_ok && valid[1]) {
         st_v2(krow, k0, k1);
@@ -123,6 +125,8 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
   __shared__ double panels[NW * RowReducer<NRC>::PANEL];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowReducer<NRC> rr(panels, warp, lane);
+  __shared__ double sexp[256];
+  load_exp_table(sexp);
   const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
 #pragma unroll
       for (int c = 0; c < kCPT; ++c) {
         FullPair<d> pr;
-        gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[c], Sj[c], qj[c], jit2, &pr);
+        gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[c], Sj[c], qj[c], jit2, sexp, &pr);
         const double gk0 = valid[c] ? gv[c] * pr.k : 0.0;
         acc_scale += gk0;
         const double gk = gk0 * s;

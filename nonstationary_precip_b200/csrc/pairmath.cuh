@@ -12,6 +12,8 @@
 #pragma once
 #include <math.h>
 
+#include "exp_table.cuh"
+
 #if defined(__CUDACC__)
 #define NPGP_HD __host__ __device__ __forceinline__
 #else
@@ -31,6 +33,38 @@ NPGP_HD double fast_rsqrt(double x) {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
+// exp(x) for x <= 0 (the only case on this path: K = prefactor * exp(-Q)).  Table-driven: x = (256 k + j) ln2/256 + r,
+// |r| <= ln2/512, exp(x) = 2^k * 2^(j/256) * (1 + r + r^2/2 + r^3/6 + r^4/24)  (remainder r^5/120 < 4e-17).  About 10 FP64
+// instructions instead of ~25-30 for the library exp -- the Gibbs / RBF tile kernels are FP64-pipe bound and spend one
+// exp per pair.  `tab` is the 256-entry table of 2^(j/256) (in shared memory on the device).
+NPGP_HD double exp_neg(double x, const double* tab) {
+#if defined(__CUDA_ARCH__)
+  if (x < -708.0) return 0.0;
+  const double t = fma(x, kInvLn2x256, 6755399441055744.0);  // 2^52 + 2^51: the integer lands in the low mantissa bits
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double r = fma(nd, -kLn2d256Hi, x);
+  r = fma(nd, -kLn2d256Lo, r);
+  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double v = tab[n & 255] * p;  // in [1, 2) up to rounding
+  return __hiloint2double(__double2hiint(v) + ((n >> 8) << 20), __double2loint(v));  // * 2^k through the exponent field
+#else
+  (void)tab;
+  return exp(x);
+#endif
+}
+
+NPGP_HD double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
 constexpr int sym_size(int d) { return d * (d + 1) / 2; }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -46,7 +80,7 @@ struct DiagPair {
 // xi, ai = l_i^2, ci as above (row point); zj, bj, cj (column point)
 template <int D>
 NPGP_HD double gibbs_diag_eval(const double* xi, const double* ai, double ci, const double* zj, const double* bj,
-                               double cj, DiagPair<D>* out = nullptr) {
+                               double cj, const double* etab, DiagPair<D>* out = nullptr) {
   double s[D], dl[D], pre[D + 1], suf[D + 1];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
@@ -69,7 +103,7 @@ NPGP_HD double gibbs_diag_eval(const double* xi, const double* ai, double ci, co
   }
   const double r = fast_rsqrt(P);
   const double r2 = r * r;
-  const double k = (ci * cj) * r * exp(-num * r2);
+  const double k = (ci * cj) * r * exp_neg(-num * r2, etab);
   if (out) {
     out->k = k;
 #pragma unroll
@@ -143,7 +177,7 @@ struct FullPair {
 // xi, Si (packed), qi = det(Si)^(1/4); likewise column point.  jit2 = 2 * jitter.
 template <int d>
 NPGP_HD double gibbs_full_eval(const double* xi, const double* Si, double qi, const double* zj, const double* Sj,
-                               double qj, double jit2, FullPair<d>* out = nullptr) {
+                               double qj, double jit2, const double* etab, FullPair<d>* out = nullptr) {
   constexpr int P = sym_size(d);
   double At[P], Bt[P], adjA[P], adjB[P], detA, detB, dl[d], v[d];
 #pragma unroll
@@ -162,11 +196,11 @@ NPGP_HD double gibbs_full_eval(const double* xi, const double* Si, double qi, co
   double dv = 0.0;
 #pragma unroll
   for (int k = 0; k < d; ++k) dv = fma(dl[k], v[k], dv);
-  const double idetB2 = 2.0 / detB;
+  const double idetB2 = 2.0 * fast_rcp(detB);
   const double r = fast_rsqrt(detA);
   // det(A)^(-1/2) = 2^(d/2) rsqrt(det At)
   const double pow2 = (d == 2) ? 2.0 : 2.8284271247461900976;
-  const double k = (qi * qj) * (pow2 * r) * exp(-dv * idetB2);
+  const double k = (qi * qj) * (pow2 * r) * exp_neg(-dv * idetB2, etab);
   if (out) {
     out->k = k;
     const double hr2 = 0.5 * r * r;
