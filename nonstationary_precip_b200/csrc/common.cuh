@@ -107,6 +107,54 @@ struct GSpec {
   const double* colvec;
 };
 
+// Register queue that keeps the upstream-gradient entries G[i .. i+DEPTH-1, columns of this thread] in flight, so that
+// the global-load latency of the backward kernels' one G read per pair is covered by DEPTH rows of pair math.
+#ifndef NPGP_GPF_DEPTH
+#define NPGP_GPF_DEPTH 4
+#endif
+template <int CPT, int DEPTH = NPGP_GPF_DEPTH>
+struct GPrefetch {
+  const double* base;  // &G[0, jbase] or nullptr
+  long ldg;
+  int row_end;
+  bool v[CPT], vec;
+  double q[DEPTH][CPT];
+  __device__ __forceinline__ GPrefetch(const GSpec& g, int jbase, const bool* valid, int vec_ok, int row_begin,
+                                       int row_end_)
+      : base(g.Gm ? g.Gm + jbase : nullptr), ldg(g.ldg), row_end(row_end_) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) v[c] = valid[c];
+    vec = (CPT == 2) && vec_ok && valid[CPT - 1];
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) fetch(row_begin + k, q[k]);
+  }
+  __device__ __forceinline__ void fetch(int i, double* out) const {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) out[c] = 0.0;
+    if (base == nullptr || i >= row_end) return;
+    const double* grow = base + (long)i * ldg;
+    if (vec) {
+      const double2 t = *reinterpret_cast<const double2*>(grow);
+      out[0] = t.x;
+      out[CPT - 1] = t.y;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        if (v[c]) out[c] = grow[c];
+    }
+  }
+  // returns row i's entries and issues the load of row i + DEPTH
+  __device__ __forceinline__ void pop(int i, double* out) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) out[c] = q[0][c];
+#pragma unroll
+    for (int k = 0; k + 1 < DEPTH; ++k)
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) q[k][c] = q[k + 1][c];
+    fetch(i + DEPTH, q[DEPTH - 1]);
+  }
+};
+
 // rows handled by one CTA: enough CTAs for `waves_target` CTAs per SM, at least one staged chunk each
 static inline int pick_rows_per_cta(int n1, int col_tiles, int waves_target) {
   long want = (long)kNumSMs * waves_target;

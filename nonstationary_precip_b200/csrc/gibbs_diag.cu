@@ -5,6 +5,7 @@
 // 512 contiguous bytes of a row) and walks down rows.  Per-column data (z, l^2, c) lives in registers, per-row data is
 // staged in shared memory 32 rows at a time and read by broadcast.  The kernel is store-only in the forward direction
 // (8 B / pair) and FP64-pipe co-limited (about 40 DP instructions per pair at D=3).
+#include <cstdlib>
 #include "common.cuh"
 #include "pairmath.cuh"
 
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_fwd_kernel(int n1, int n2, con
 }
 
 
-template <int D, bool DX1, bool DX2>
+template <int D, bool DX1, bool DX2, int CPT>
 __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, const double* __restrict__ x1,
                                                              const double* __restrict__ ell1,
                                                              const double* __restrict__ x2,
@@ -109,15 +110,15 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
   RowReducer<NRC> rr(panels, warp, lane);
   __shared__ double sexp[256];
   load_exp_table(sexp);
-  const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
+  const int jbase = blockIdx.y * (kNT * CPT) + threadIdx.x * CPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
   const double s = scale ? *scale : 1.0;
 
-  double z[kCPT][D], b[kCPT][D], cj[kCPT], cv[kCPT];
-  bool valid[kCPT];
+  double z[CPT][D], b[CPT][D], cj[CPT], cv[CPT];
+  bool valid[CPT];
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     const int j = jbase + c;
     valid[c] = j < n2;
     double prod = 1.0;
@@ -131,14 +132,15 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
     cj[c] = sqrt(prod);
     cv[c] = (g.colvec && valid[c]) ? g.colvec[j] : 0.0;
   }
-  double cw[kCPT][D], cs0[kCPT], cxz[kCPT][D];
+  double cw[CPT][D], cs0[CPT], cxz[CPT][D];
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     cs0[c] = 0.0;
 #pragma unroll
     for (int d = 0; d < D; ++d) cw[c][d] = cxz[c][d] = 0.0;
   }
   double acc_scale = 0.0;
+  GPrefetch<CPT> gq(g, jbase, valid, vec_ok, row_begin, row_end);
 
   for (int i0 = row_begin; i0 < row_end; i0 += kTI) {
     __syncthreads();
@@ -151,27 +153,15 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
     __syncthreads();
     const int nr = min(kTI, row_end - i0);
     for (int r = 0; r < nr; ++r) {
-      double gv[kCPT] = {0.0, 0.0};
-      if (g.Gm) {
-        const double* grow = g.Gm + (long)(i0 + r) * g.ldg + jbase;
-        if (vec_ok && valid[1]) {
-          const double2 t = *reinterpret_cast<const double2*>(grow);
-          gv[0] = t.x;
-          gv[1] = t.y;
-        } else {
-          if (valid[0]) gv[0] = grow[0];
-          if (valid[1]) gv[1] = grow[1];
-        }
-        gv[0] *= srs[r];
-        gv[1] *= srs[r];
-      }
-      gv[0] = fma(srv[r], cv[0], gv[0]);
-      gv[1] = fma(srv[r], cv[1], gv[1]);
+      double gv[CPT];
+      gq.pop(i0 + r, gv);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) gv[c] = fma(srv[r], cv[c], gv[c] * srs[r]);
       double rw[D], rxz[D], rs0 = 0.0;
 #pragma unroll
       for (int d = 0; d < D; ++d) rw[d] = rxz[d] = 0.0;
 #pragma unroll
-      for (int c = 0; c < kCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         DiagPair<D> p;
         gibbs_diag_eval<D>(sx[r], sa[r], sc[r], z[c], b[c], cj[c], sexp, &p);
         const double gk0 = valid[c] ? gv[c] * p.k : 0.0;  // dL/ds contribution (unscaled kernel)
@@ -222,7 +212,7 @@ __global__ void __launch_bounds__(kNT) gibbs_diag_bwd_kernel(int n1, int n2, con
   }
   // column-side: one atomic per (column, component) per CTA
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     if (!valid[c]) continue;
     const int j = jbase + c;
 #pragma unroll
@@ -254,17 +244,17 @@ static int launch_fwd(int n1, int n2, const double* x1, const double* ell1, cons
   return NPGP_OK;
 }
 
-template <int D>
-static int launch_bwd(int n1, int n2, const double* x1, const double* ell1, const double* x2, const double* ell2,
-                      const double* scale, GSpec g, double* d_ell1, double* d_x1, double* d_ell2, double* d_x2,
-                      double* d_scale, cudaStream_t st) {
-  const int col_tiles = ceil_div(n2, kTJ);
+template <int D, int CPT>
+static int launch_bwd_cpt(int n1, int n2, const double* x1, const double* ell1, const double* x2, const double* ell2,
+                          const double* scale, GSpec g, double* d_ell1, double* d_x1, double* d_ell2, double* d_x2,
+                          double* d_scale, cudaStream_t st) {
+  const int col_tiles = ceil_div(n2, kNT * CPT);
   const int rpc = pick_rows_per_cta(n1, col_tiles, 8);
   dim3 grid(ceil_div(n1, rpc), col_tiles);
   const int vec_ok = g.Gm ? ((g.ldg % 2 == 0) && ((reinterpret_cast<uintptr_t>(g.Gm) & 15) == 0)) : 0;
-#define NPGP_L(A, B)                                                                                              \
-  gibbs_diag_bwd_kernel<D, A, B><<<grid, kNT, 0, st>>>(n1, n2, x1, ell1, x2, ell2, scale, g, vec_ok, d_ell1, d_x1, \
-                                                       d_ell2, d_x2, d_scale, rpc)
+#define NPGP_L(A, B)                                                                                             \
+  gibbs_diag_bwd_kernel<D, A, B, CPT><<<grid, kNT, 0, st>>>(n1, n2, x1, ell1, x2, ell2, scale, g, vec_ok, d_ell1, \
+                                                            d_x1, d_ell2, d_x2, d_scale, rpc)
   if (d_x1 && d_x2) NPGP_L(true, true);
   else if (d_x1) NPGP_L(true, false);
   else if (d_x2) NPGP_L(false, true);
@@ -272,6 +262,16 @@ static int launch_bwd(int n1, int n2, const double* x1, const double* ell1, cons
 #undef NPGP_L
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
+}
+
+template <int D>
+static int launch_bwd(int n1, int n2, const double* x1, const double* ell1, const double* x2, const double* ell2,
+                      const double* scale, GSpec g, double* d_ell1, double* d_x1, double* d_ell2, double* d_x2,
+                      double* d_scale, cudaStream_t st) {
+  static const int cpt = getenv("NPGP_DIAG_BWD_CPT") ? atoi(getenv("NPGP_DIAG_BWD_CPT")) : 2;
+  if (cpt == 1)
+    return launch_bwd_cpt<D, 1>(n1, n2, x1, ell1, x2, ell2, scale, g, d_ell1, d_x1, d_ell2, d_x2, d_scale, st);
+  return launch_bwd_cpt<D, 2>(n1, n2, x1, ell1, x2, ell2, scale, g, d_ell1, d_x1, d_ell2, d_x2, d_scale, st);
 }
 
 }  // namespace npgp

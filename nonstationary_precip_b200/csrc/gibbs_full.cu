@@ -9,6 +9,7 @@
 // Sigma is passed packed symmetric, (n, d(d+1)/2) row-major: d=2 [00,01,11], d=3 [00,01,02,11,12,22].
 // Gradients w.r.t. Sigma are returned in the same packing and hold the entries of the SYMMETRIC matrix dL/dSigma
 // (so dL = sum_k G_kk dS_kk + 2 sum_{k<l} G_kl dS_kl).
+#include <cstdlib>
 #include "common.cuh"
 #include "pairmath.cuh"
 
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kNT) gibbs_full_fwd_kernel(int n1, int n2, con
 }
 
 
-template <int d, bool DX1, bool DX2>
+template <int d, bool DX1, bool DX2, int CPT>
 __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, const double* __restrict__ x1,
                                                              const double* __restrict__ S1,
                                                              const double* __restrict__ x2,
@@ -127,20 +128,20 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
   RowReducer<NRC> rr(panels, warp, lane);
   __shared__ double sexp[256];
   load_exp_table(sexp);
-  const int jbase = blockIdx.y * kTJ + threadIdx.x * kCPT;
+  const int jbase = blockIdx.y * (kNT * CPT) + threadIdx.x * CPT;
   const int row_begin = blockIdx.x * rows_per_cta;
   const int row_end = min(n1, row_begin + rows_per_cta);
   const double s = scale ? *scale : 1.0;
-  double z[kCPT][d], Sj[kCPT][P], qj[kCPT], cv[kCPT];
-  bool valid[kCPT];
+  double z[CPT][d], Sj[CPT][P], qj[CPT], cv[CPT];
+  bool valid[CPT];
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     load_col_full<d>(n2, jbase + c, x2, S2, z[c], Sj[c], qj[c], valid[c]);
     cv[c] = (g.colvec && valid[c]) ? g.colvec[jbase + c] : 0.0;
   }
-  double cW[kCPT][P], cs0[kCPT], cxz[kCPT][d];
+  double cW[CPT][P], cs0[CPT], cxz[CPT][d];
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     cs0[c] = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) cW[c][p] = 0.0;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
     for (int k = 0; k < d; ++k) cxz[c][k] = 0.0;
   }
   double acc_scale = 0.0;
+  GPrefetch<CPT> gq(g, jbase, valid, vec_ok, row_begin, row_end);
 
   for (int i0 = row_begin; i0 < row_end; i0 += kTI) {
     __syncthreads();
@@ -160,29 +162,17 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
     __syncthreads();
     const int nr = min(kTI, row_end - i0);
     for (int r = 0; r < nr; ++r) {
-      double gv[kCPT] = {0.0, 0.0};
-      if (g.Gm) {
-        const double* grow = g.Gm + (long)(i0 + r) * g.ldg + jbase;
-        if (vec_ok && valid[1]) {
-          const double2 t = *reinterpret_cast<const double2*>(grow);
-          gv[0] = t.x;
-          gv[1] = t.y;
-        } else {
-          if (valid[0]) gv[0] = grow[0];
-          if (valid[1]) gv[1] = grow[1];
-        }
-        gv[0] *= srs[r];
-        gv[1] *= srs[r];
-      }
-      gv[0] = fma(srv[r], cv[0], gv[0]);
-      gv[1] = fma(srv[r], cv[1], gv[1]);
+      double gv[CPT];
+      gq.pop(i0 + r, gv);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) gv[c] = fma(srv[r], cv[c], gv[c] * srs[r]);
       double rW[P], rxz[d], rs0 = 0.0;
 #pragma unroll
       for (int p = 0; p < P; ++p) rW[p] = 0.0;
 #pragma unroll
       for (int k = 0; k < d; ++k) rxz[k] = 0.0;
 #pragma unroll
-      for (int c = 0; c < kCPT; ++c) {
+      for (int c = 0; c < CPT; ++c) {
         FullPair<d> pr;
         gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[c], Sj[c], qj[c], jit2, sexp, &pr);
         const double gk0 = valid[c] ? gv[c] * pr.k : 0.0;
@@ -241,7 +231,7 @@ __global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, con
     }
   }
 #pragma unroll
-  for (int c = 0; c < kCPT; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     if (!valid[c]) continue;
     const int j = jbase + c;
     double adj[P], det;
@@ -345,17 +335,17 @@ static int launch_full_fwd(int n1, int n2, const double* x1, const double* S1, c
   return NPGP_OK;
 }
 
-template <int d>
-static int launch_full_bwd(int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
-                           double jitter, const double* scale, GSpec g, double* d_S1, double* d_x1, double* d_S2,
-                           double* d_x2, double* d_scale, cudaStream_t st) {
-  const int col_tiles = ceil_div(n2, kTJ);
+template <int d, int CPT>
+static int launch_full_bwd_cpt(int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
+                               double jitter, const double* scale, GSpec g, double* d_S1, double* d_x1, double* d_S2,
+                               double* d_x2, double* d_scale, cudaStream_t st) {
+  const int col_tiles = ceil_div(n2, kNT * CPT);
   const int rpc = pick_rows_per_cta(n1, col_tiles, 8);
   dim3 grid(ceil_div(n1, rpc), col_tiles);
   const int vec_ok = g.Gm ? ((g.ldg % 2 == 0) && ((reinterpret_cast<uintptr_t>(g.Gm) & 15) == 0)) : 0;
-#define NPGP_L(A, B)                                                                                                \
-  gibbs_full_bwd_kernel<d, A, B><<<grid, kNT, 0, st>>>(n1, n2, x1, S1, x2, S2, 2.0 * jitter, scale, g, vec_ok, d_S1, \
-                                                       d_x1, d_S2, d_x2, d_scale, rpc)
+#define NPGP_L(A, B)                                                                                               \
+  gibbs_full_bwd_kernel<d, A, B, CPT><<<grid, kNT, 0, st>>>(n1, n2, x1, S1, x2, S2, 2.0 * jitter, scale, g, vec_ok, \
+                                                            d_S1, d_x1, d_S2, d_x2, d_scale, rpc)
   if (d_x1 && d_x2) NPGP_L(true, true);
   else if (d_x1) NPGP_L(true, false);
   else if (d_x2) NPGP_L(false, true);
@@ -363,6 +353,16 @@ static int launch_full_bwd(int n1, int n2, const double* x1, const double* S1, c
 #undef NPGP_L
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
+}
+
+template <int d>
+static int launch_full_bwd(int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
+                           double jitter, const double* scale, GSpec g, double* d_S1, double* d_x1, double* d_S2,
+                           double* d_x2, double* d_scale, cudaStream_t st) {
+  static const int cpt = getenv("NPGP_FULL_BWD_CPT") ? atoi(getenv("NPGP_FULL_BWD_CPT")) : 2;
+  if (cpt == 2)
+    return launch_full_bwd_cpt<d, 2>(n1, n2, x1, S1, x2, S2, jitter, scale, g, d_S1, d_x1, d_S2, d_x2, d_scale, st);
+  return launch_full_bwd_cpt<d, 1>(n1, n2, x1, S1, x2, S2, jitter, scale, g, d_S1, d_x1, d_S2, d_x2, d_scale, st);
 }
 
 }  // namespace npgp
