@@ -397,15 +397,34 @@ class GaussEllBatchedFn(torch.autograd.Function):
         return None, d * gmu, d * gvar, dnoise
 
 
+def rbfper_fwd(t1, t2, hyp, out=None):
+    """K = s * RBF(t1,t2) * Periodic(t1,t2) on 1-D inputs; hyp = [l_rbf, l_per, period, s] (4,).  `out` may be a strided
+    view (e.g. the left half of a wider feature matrix)."""
+    t1, t2, hyp = _c(t1.reshape(-1)), _c(t2.reshape(-1)), _c(hyp)
+    K = out if out is not None else torch.empty(t1.numel(), t2.numel(), dtype=torch.float64, device=t1.device)
+    check(lib().npgp_rbfper_fwd(t1.numel(), t2.numel(), ptr(t1), ptr(t2), ptr(hyp), ptr(K), K.stride(0), stream()),
+          "npgp_rbfper_fwd")
+    return K
+
+
+def rbfper_bwd(t1, t2, hyp, G, need_dt2=False):
+    """Gradients of sum(G * K) w.r.t. hyp (4,) and optionally t2.  G may be a strided view (row stride G.stride(0))."""
+    t1, t2, hyp = _c(t1.reshape(-1)), _c(t2.reshape(-1)), _c(hyp)
+    assert G.stride(1) == 1
+    out4 = torch.zeros(4, dtype=torch.float64, device=G.device)
+    dt2 = torch.zeros_like(t2) if need_dt2 else None
+    check(lib().npgp_rbfper_bwd(t1.numel(), t2.numel(), ptr(t1), ptr(t2), ptr(hyp), ptr(G), G.stride(0), ptr(out4),
+                                ptr(dt2), stream()), "npgp_rbfper_bwd")
+    return out4, dt2
+
+
 class RbfPerFn(torch.autograd.Function):
     """K = s * RBF(t1,t2) * Periodic(t1,t2) on 1-D inputs; hyp = [l_rbf, l_per, period, s] (4,).  Gradients to hyp, t2."""
 
     @staticmethod
     def forward(ctx, t1, t2, hyp):
         t1c, t2c, hc = t1.detach().contiguous().reshape(-1), t2.detach().contiguous().reshape(-1), hyp.detach().contiguous()
-        K = torch.empty(t1c.numel(), t2c.numel(), dtype=torch.float64, device=t1.device)
-        check(lib().npgp_rbfper_fwd(t1c.numel(), t2c.numel(), ptr(t1c), ptr(t2c), ptr(hc), ptr(K), K.stride(0), stream()),
-              "npgp_rbfper_fwd")
+        K = rbfper_fwd(t1c, t2c, hc)
         ctx.save_for_backward(t1c, t2c, hc)
         ctx.t2_shape = t2.shape
         return K
@@ -413,11 +432,7 @@ class RbfPerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, G):
         t1, t2, hyp = ctx.saved_tensors
-        G = G.contiguous()
-        out4 = torch.zeros(4, dtype=torch.float64, device=G.device)
-        dt2 = torch.zeros_like(t2) if ctx.needs_input_grad[1] else None
-        check(lib().npgp_rbfper_bwd(t1.numel(), t2.numel(), ptr(t1), ptr(t2), ptr(hyp), ptr(G), G.stride(0), ptr(out4),
-                                    ptr(dt2), stream()), "npgp_rbfper_bwd")
+        out4, dt2 = rbfper_bwd(t1, t2, hyp, G.contiguous(), need_dt2=ctx.needs_input_grad[1])
         return None, (dt2.reshape(ctx.t2_shape) if dt2 is not None else None), out4
 
 

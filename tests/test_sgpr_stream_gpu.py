@@ -84,3 +84,39 @@ def test_streamed_sgpr_rank_sharding_by_emulated_all_reduce():
     assert abs(l0.item() - l_full.item()) < 1e-10 * abs(l_full.item())
     assert rel(r0.log_ell_z.grad, full.log_ell_z.grad) < 1e-8
     assert rel(r0.Z.grad, full.Z.grad) < 1e-8
+
+
+@pytest.mark.parametrize("n,M,chunk", [(500, 24, 192), (900, 40, 900)])
+def test_streamed_spatio_temporal_sgpr_matches_dense_oracle(n, M, chunk):
+    """Config-3 model (Nystrom RBF x Periodic on time + scaled Nystrom Gibbs on lon/lat, one inducing set) evaluated
+    matrix free, against the oracle's dense rank-2M bound (spatio_temporal_models.py:35-60)."""
+    from nonstationary_precip_b200.sgpr import SGPRSpatioTemporalStream, _inv_softplus
+    g = torch.Generator().manual_seed(n + M)
+    x = torch.cat([torch.rand(n, 1, generator=g) * 6 - 3, torch.rand(n, 2, generator=g) * 2 - 1], 1)
+    y = torch.sin(2 * math.pi * x[:, 0] / 1.7) * torch.exp(-(x[:, 1:] ** 2).sum(-1)) + 0.1 * torch.randn(n, generator=g)
+    Z = x[torch.randperm(n, generator=g)[:M]].clone()
+    le = math.log(0.4) + 0.2 * torch.randn(2, M, generator=g)
+    c, os_, lam = torch.full((2,), math.log(0.4)), torch.ones(2), torch.full((2, 2), 1.3)
+    hyp0 = (0.9, 1.3, 1.7, 7.6)
+    model = SGPRSpatioTemporalStream(Z.cuda(), le.cuda(), c.cuda(), os_.cuda(), lam.cuda(), hyp_t=hyp0,
+                                     outputscale_s=0.8, noise=0.05)
+    loss = model.neg_objective_and_grad(x.cuda(), y.cuda(), chunk=chunk)
+
+    Zc, lec = Z.clone().requires_grad_(True), le.clone().requires_grad_(True)
+    raw = torch.tensor([_inv_softplus(hyp0[0]), _inv_softplus(hyp0[1]), _inv_softplus(hyp0[2]),
+                        _inv_softplus(hyp0[3] - 7.0)], requires_grad=True)
+    ro = torch.tensor(_inv_softplus(0.8), requires_grad=True)
+    rn = torch.tensor(_inv_softplus(0.05 - 1e-4), requires_grad=True)
+    sp = o.softplus(raw)
+    hyp = torch.stack([sp[0], sp[1], sp[2], 7.0 + sp[3]])
+    # the temporal kernel's inducing points are a frozen alias of Z: no gradient through column 0
+    Zo = torch.cat([Zc[:, :1].detach(), Zc[:, 1:]], 1)
+    want = -o.st_sgpr_objective(x, y, Zo, lec, hyp, o.softplus(ro), 1e-4 + o.softplus(rn), c, os_, lam)
+    want.backward()
+    assert abs(loss.item() - want.item()) < 1e-8 * abs(want.item())
+    assert rel(model.log_ell_z.grad, lec.grad) < 1e-5
+    assert rel(model.Z.grad, Zc.grad) < 1e-5
+    assert float(model.Z.grad[:, 0].abs().max()) == 0.0
+    assert rel(model.raw_hyp_t.grad, raw.grad) < 1e-5
+    assert rel(model.raw_outputscale.grad.reshape(()), ro.grad) < 1e-6
+    assert rel(model.raw_noise.grad.reshape(()), rn.grad) < 1e-6
