@@ -141,8 +141,47 @@ def sparse_multivariate_cases():
         prior_H_log_prob=logp)
 
 
+def dataprep_and_metrics_cases():
+    """The reference's utils/dataprep.py:9-52 and utils/metrics.py:37-54 / metrics2.py:36-47 run on its own data fixture
+    data/uib_spatial.csv (394 rows: lon, lat, tp), plus the split of experiments/spatial_exp.py:126-141 for i = 0.
+    The raw table is stored too: it is the input of BASELINE config 1 and /root/reference does not exist on the GPU box."""
+    torch.set_default_dtype(torch.float32)
+    dp = importlib.import_module("utils.dataprep")
+    m1 = importlib.import_module("utils.metrics")
+    m2 = importlib.import_module("utils.metrics2")
+    path = os.path.join(REF, "data", "uib_spatial.csv")
+    import pandas as pd
+    raw = np.asarray(pd.read_csv(path, dtype=np.float64))
+    data = dp.download_data(path)
+    x_in = dp.prep_inputs(data)
+    y_bc, bc_lam = dp.prep_outputs(data)
+    xw, yw, meanx, stdx, meany, stdy = dp.whitening_transform(data)
+    trx, try_, tex, tey = dp.train_test_split(xw, yw, 0.8)
+    # spatial_exp.py:126-141 in float64 (load_khyber_data, :36-40), split i = 0
+    x64, y64 = torch.tensor(raw[:, 0:2]), torch.tensor(raw[:, -1])
+    sx, mx = torch.std_mean(x64, dim=-2)
+    sy, my = torch.std_mean(y64)
+    rng = np.random.default_rng(173 + 0)
+    idx = np.arange(0, y64.shape[0], 1)
+    rng.shuffle(idx)
+    # metrics on a fixed synthetic prediction
+    g = torch.Generator().manual_seed(7)
+    yt = torch.randn(40, generator=g, dtype=torch.float64)
+    mu = yt + 0.3 * torch.randn(40, generator=g, dtype=torch.float64)
+    var = 0.2 + torch.rand(40, generator=g, dtype=torch.float64)
+    ystd = torch.tensor(2.5, dtype=torch.float64)
+    pred = torch.distributions.MultivariateNormal(mu, torch.diag(var))
+    npz("uib_spatial_dataprep", raw=raw, data_f32=data, prep_inputs=x_in, boxcox_y=y_bc, boxcox_lambda=np.float64(bc_lam),
+        xw=xw, yw=yw, meanx=meanx, stdx=stdx, meany=meany, stdy=stdy, split_train_x=trx, split_test_y=tey,
+        x_norm64=(x64 - mx) / sx, y_norm64=(y64 - my) / sy, stdy64=sy, shuffle_idx_seed173=idx,
+        m_y=yt, m_mu=mu, m_var=var, m_ystd=ystd, rmse1=m1.rmse(mu, yt, ystd), rmse2=m2.rmse(mu, yt, ystd),
+        nlpd1=m1.nlpd(pred, yt, ystd), nlpd_marg=m1.negative_log_predictive_density(yt, mu, var))
+    torch.set_default_dtype(torch.float64)
+
+
 if __name__ == "__main__":
     gibbs_diag_cases()
     lognormal_field_cases()
     multivariate_cases()
     sparse_multivariate_cases()
+    dataprep_and_metrics_cases()
