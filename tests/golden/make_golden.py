@@ -179,9 +179,30 @@ def dataprep_and_metrics_cases():
     torch.set_default_dtype(torch.float64)
 
 
+def spatio_temporal_data_case():
+    """Train/test tensors of experiments/spatio_temporal_exp.py:29-56 (load_uib_data + load_train_test: year 2000, months
+    1-4 train = 172 rows, month 5 test = 43 rows; float32 z-scored (time, lon, lat) and tp), obtained by running those
+    lines on data/uib_spatio_temporal.csv.  (The script itself cannot be imported: cartopy / pymc3 at module top.)"""
+    import pandas as pd
+    data = pd.read_csv(os.path.join(REF, "data", "uib_spatio_temporal.csv"))
+    data = data[data['time'] < 2001].copy()
+    data['month'] = data['time'].rank(method='dense').astype('int')
+    train_test_data = data[data['month'] < 6]
+    x, y = torch.Tensor(np.array(train_test_data))[:, 1:4], torch.Tensor(np.array(train_test_data)[:, -2])
+    with torch.no_grad():
+        stdx, meanx = torch.std_mean(x, dim=-2)
+        x_norm = (x - meanx) / stdx
+        stdy, meany = torch.std_mean(y)
+        y_norm = (y - meany) / stdy
+    split_idx = len(np.where(train_test_data['month'] < 5)[0])
+    npz("uib_spatio_temporal_2000", table=np.array(train_test_data, dtype=np.float64), x_train=x_norm[0:split_idx],
+        y_train=y_norm[0:split_idx], x_test=x_norm[split_idx:], y_test=y_norm[split_idx:], meany=meany, stdy=stdy)
+
+
 if __name__ == "__main__":
     gibbs_diag_cases()
     lognormal_field_cases()
     multivariate_cases()
     sparse_multivariate_cases()
     dataprep_and_metrics_cases()
+    spatio_temporal_data_case()

@@ -58,3 +58,25 @@ def test_spatial_exp_trains_on_real_data(inference):
     assert math.isfinite(r["rmse"]) and math.isfinite(r["nlpd"])
     # better than predicting the training mean (RMSE in raw units = stdy for the z-scored zero predictor)
     assert r["rmse"] < float(stdy)
+
+
+def test_spatio_temporal_exp_trains_on_real_data():
+    """experiments/spatio_temporal_exp.py on the reference's year-2000 table: first objective equals the oracle's
+    st_sgpr_objective at the initial parameters, training reduces it, predictions are finite."""
+    from experiments import spatio_temporal_exp as ste
+    from nonstationary_precip_b200.utils.dataprep import kmeans_inducing_points
+    args = ste.parse_args(["--n_iter", "30", "--M", "40", "--log_every", "1000"])
+    r = ste.run(args, torch.device("cuda"), log=lambda *_: None)
+    x, y, xt, yt, meany, stdy = ste.load_train_test()
+    assert x.shape == (172, 3) and xt.shape == (43, 3)
+    z = kmeans_inducing_points(40, x.cuda(), seed=173).cpu()
+    c, os_, lam = torch.full((2,), math.log(0.3), dtype=torch.float64), torch.ones(2, dtype=torch.float64), \
+        torch.full((2, 2), 1.3, dtype=torch.float64)
+    sp0 = math.log(2.0)  # softplus(0): GPyTorch's default raw parameter is 0
+    hyp = torch.tensor([sp0, sp0, sp0, 7.0 + sp0], dtype=torch.float64)
+    want = -o.st_sgpr_objective(x, y, z, torch.full((2, 40), math.log(0.3), dtype=torch.float64), hyp,
+                                torch.tensor(sp0, dtype=torch.float64), torch.tensor(1e-4 + sp0, dtype=torch.float64),
+                                c, os_, lam)
+    assert abs(r["first_loss"] - want.item()) < 1e-6 * abs(want.item())
+    assert r["last_loss"] < r["first_loss"] and r["finite"]
+    assert math.isfinite(r["rmse"]) and math.isfinite(r["nlpd"])
