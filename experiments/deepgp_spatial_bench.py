@@ -1,0 +1,106 @@
+#!/usr/bin/env python3
+"""Deep-GP benchmark of the reference (experiments/deepgp_spatial_bench.py:22-139) on the B200 kernels: `num_layers`
+DSVI layers (models/dgps.py) on the 394-row Upper-Indus-Basin table, whitening transform, shuffled 80/20 split per random
+state (sklearn.utils.shuffle as :48), Adam lr 0.01 over minibatches of 315 rows with 3 likelihood samples (:34-35,
+:66,:84), test RMSE / NLPD through `DeepGP.predict` (:97-115).  Defaults follow the script; fp64 instead of fp32.
+
+    python experiments/deepgp_spatial_bench.py [--num_epochs 400] [--num_layers 4] [--states 10]"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nonstationary_precip_b200.models import dgps as m  # noqa: E402
+from nonstationary_precip_b200.utils import dataprep as dp  # noqa: E402
+from nonstationary_precip_b200.utils.metrics2 import nlpd, rmse  # noqa: E402
+
+
+def load_table(path=None):
+    """float32 table (lon, lat, tp) as utils.dataprep.download_data returns it."""
+    if path is not None:
+        return dp.download_data(path)
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "uib_spatial_dataprep.npz"))["raw"]
+    return torch.tensor(raw, dtype=torch.float32)
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--data", default=None)
+    p.add_argument("--num_epochs", type=int, default=400)
+    p.add_argument("--num_samples", type=int, default=3)
+    p.add_argument("--num_layers", type=int, default=4)
+    p.add_argument("--states", type=int, default=10)
+    p.add_argument("--batch_size", type=int, default=315)
+    p.add_argument("--num_inducing", type=int, default=250)
+    p.add_argument("--json", default=None)
+    return p.parse_args(argv)
+
+
+def run_state(random_state, dataset, args, device):
+    from sklearn.utils import shuffle
+    data = shuffle(dataset, random_state=random_state)
+    x_tr, y_tr, meanx, stdx, meany, stdy = dp.whitening_transform(data)
+    train_x, train_y, test_x, test_y = (t.double().to(device) for t in dp.train_test_split(x_tr, y_tr, 0.8))
+    torch.manual_seed(random_state)
+    model = m.DeepGP(args.num_layers, train_x.shape, num_inducing=args.num_inducing).to(device).double()
+    mll = m.DeepApproximateMLL(m.VariationalELBO(model.likelihood, model, train_x.shape[-2]))
+    train_loader = DataLoader(TensorDataset(train_x, train_y), batch_size=args.batch_size, shuffle=True)
+    model.train()
+    optimizer = torch.optim.Adam([{"params": model.parameters()}], lr=0.01)
+    losses, step = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.num_epochs):
+        for x_batch, y_batch in train_loader:
+            with m.num_likelihood_samples(args.num_samples):
+                optimizer.zero_grad()
+                output = model(x_batch, seed=1000 * random_state + step)
+                loss = -mll(output, y_batch)
+                loss.backward()
+                optimizer.step()
+            losses.append(loss.item())
+            step += 1
+    torch.cuda.synchronize()
+    train_s = time.perf_counter() - t0
+    test_loader = DataLoader(TensorDataset(test_x, test_y), batch_size=args.batch_size)
+    model.eval()
+    with torch.no_grad(), m.num_likelihood_samples(args.num_samples):
+        pred_y, y_means, y_var, test_lls = model.predict(test_loader)
+    # RMSE on the sample-averaged predictive mean; NLPD from the per-point log marginals that `predict` returns (the
+    # DSVI layers here carry marginals only, so the script's joint `pred_y.log_prob` (:112) is replaced by their sum)
+    rmse_test = float(rmse(y_means.mean(0) if y_means.dim() > 1 else y_means, test_y, stdy))
+    nlpd_test = float((-(test_lls.mean() - torch.log(stdy.double().to(device)))))
+    return dict(random_state=random_state, rmse=rmse_test, nlpd=nlpd_test, first_loss=losses[0], last_loss=losses[-1],
+                steps=step, train_s=train_s, steps_per_s=step / train_s)
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    if not torch.cuda.is_available():
+        raise RuntimeError("experiments/deepgp_spatial_bench.py needs a CUDA device (the models have no CPU path)")
+    dataset = load_table(args.data)
+    res = []
+    for rs in range(args.states):
+        r = run_state(rs, dataset, args, torch.device("cuda"))
+        print("random_state = %d  RMSE: %.4f, NLPD: %.4f  (%.1f steps/s)" % (rs, r["rmse"], r["nlpd"], r["steps_per_s"]))
+        res.append(r)
+    rm, nl = np.array([r["rmse"] for r in res]), np.array([r["nlpd"] for r in res])
+    print(rm.mean(), "+-", rm.std() / np.sqrt(len(res)))
+    print(nl.mean(), "+-", nl.std() / np.sqrt(len(res)))
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(dict(args=vars(args), states=res), f, indent=1)
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -80,3 +80,11 @@ def test_spatio_temporal_exp_trains_on_real_data():
     assert abs(r["first_loss"] - want.item()) < 1e-6 * abs(want.item())
     assert r["last_loss"] < r["first_loss"] and r["finite"]
     assert math.isfinite(r["rmse"]) and math.isfinite(r["nlpd"])
+
+
+def test_deepgp_spatial_bench_trains_on_real_data():
+    from experiments import deepgp_spatial_bench as dg
+    args = dg.parse_args(["--num_epochs", "15", "--num_layers", "2", "--states", "1", "--num_inducing", "64"])
+    r = dg.run_state(0, dg.load_table(), args, torch.device("cuda"))
+    assert r["steps"] == 15 and r["last_loss"] < r["first_loss"]
+    assert math.isfinite(r["rmse"]) and math.isfinite(r["nlpd"]) and r["rmse"] > 0
