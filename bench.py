@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--exec", default="graph", choices=["graph", "eager"],
                     help="replay the step as a captured CUDA graph (default) or launch it eagerly")
-    ap.add_argument("--ref-rows", type=int, default=2048, help="minibatch rows the CPU reference processes per step")
+    ap.add_argument("--ref-rows", type=int, default=16384, help="minibatch rows the CPU reference processes per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,6 +43,51 @@ class num_likelihood_samples:
         return False
 
 
+class sample_shard:
+    """Multi-GPU DSVI: the S likelihood samples are split over `world` ranks, rank r propagating samples
+    [r S/world, (r+1) S/world).  The Philox draws are keyed by the element index in the GLOBAL (S, B, width) tensor, so
+    the union of the ranks' draws is exactly the single-rank draw, and `DeepApproximateMLL` weights the local mean by
+    1/world: summing loss and gradients over ranks (one all-reduce, `allreduce_gradients`) reproduces the single-rank
+    step for every world size that divides S."""
+    _rank, _world = 0, 1
+
+    def __init__(self, rank, world):
+        self.rank_, self.world_, self.prev = int(rank), int(world), None
+
+    @classmethod
+    def local_samples(cls):
+        S = num_likelihood_samples.value()
+        if S % cls._world:
+            raise ValueError("num_likelihood_samples (%d) must be divisible by the number of ranks (%d)" % (S, cls._world))
+        return S // cls._world
+
+    def __enter__(self):
+        self.prev = (sample_shard._rank, sample_shard._world)
+        sample_shard._rank, sample_shard._world = self.rank_, self.world_
+
+    def __exit__(self, *exc):
+        sample_shard._rank, sample_shard._world = self.prev
+        return False
+
+
+def _dsvi_draw(dist, eps, seed):
+    """Sample the previous layer's marginals; offset = this rank's position in the global sample tensor."""
+    return ops.dsvi_sample(dist.mean, dist.variance, eps, seed, sample_shard._rank * dist.mean.numel())
+
+
+def allreduce_gradients(model, all_reduce):
+    """Sum the gradients of all parameters over ranks with ONE collective on a flat buffer (`all_reduce(t)` sums the
+    tensor in place, e.g. torch.distributed.all_reduce)."""
+    ps = [p for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    all_reduce(flat)
+    off = 0
+    for p in ps:
+        p.grad.copy_(flat[off:off + p.numel()].reshape(p.shape))
+        off += p.numel()
+    return flat.numel()
+
+
 class MarginalNormal:
     """Independent normal marginals (mean, variance of shape (..., B[, O])) -- all that DSVI propagates."""
 
@@ -121,7 +166,7 @@ class DeepGPLayer(Module):
     def __call__(self, inputs, are_samples=False, eps=None, seed=0, **kwargs):
         deterministic_inputs = not are_samples
         if isinstance(inputs, MarginalNormal):  # DSVI: sample the previous layer's marginals
-            inputs = ops.dsvi_sample(inputs.mean, inputs.variance, eps, seed, 0)
+            inputs = _dsvi_draw(inputs, eps, seed)
             deterministic_inputs = False
         lead = inputs.shape[:-1]
         X = inputs.reshape(-1, inputs.shape[-1]).contiguous()
@@ -133,7 +178,7 @@ class DeepGPLayer(Module):
             out = MarginalNormal(torch.stack(ms, -1).reshape(*lead, self.output_dims),
                                  torch.stack(vs, -1).reshape(*lead, self.output_dims))
         if deterministic_inputs:  # expand to S likelihood samples (same marginals for every sample)
-            S = num_likelihood_samples.value()
+            S = sample_shard.local_samples()
             out = MarginalNormal(out.mean.unsqueeze(0).expand(S, *out.mean.shape),
                                  out.variance.unsqueeze(0).expand(S, *out.variance.shape))
         return out
@@ -165,8 +210,8 @@ class DeepGPHiddenLayer(DeepGPLayer):
         """Concatenation-based skip connections, as in the reference (:53-70)."""
         if len(other_inputs):
             if isinstance(x, MarginalNormal):
-                x = ops.dsvi_sample(x.mean, x.variance, None, kwargs.get("seed", 0), 0)
-            processed = [inp.unsqueeze(0).expand(num_likelihood_samples.value(), *inp.shape) for inp in other_inputs]
+                x = _dsvi_draw(x, None, kwargs.get("seed", 0))
+            processed = [inp.unsqueeze(0).expand(sample_shard.local_samples(), *inp.shape) for inp in other_inputs]
             x = torch.cat([x] + processed, dim=-1)
         return super().__call__(x, are_samples=bool(len(other_inputs)), **kwargs)
 
@@ -244,4 +289,4 @@ class DeepApproximateMLL(Module):
         self.base_mll = base_mll
 
     def forward(self, output, target):
-        return self.base_mll(output, target).mean(0)
+        return self.base_mll(output, target).mean(0) / sample_shard._world

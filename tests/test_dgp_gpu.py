@@ -87,3 +87,40 @@ def test_dsvi_sampling_kernel_statistics_and_determinism():
     z = (h1 - 2.0) / 0.5
     assert abs(z.mean().item()) < 5e-3 and abs(z.var().item() - 1.0) < 5e-3
     assert abs((z ** 3).mean().item()) < 2e-2 and abs((z ** 4).mean().item() - 3.0) < 5e-2
+
+
+def test_dgp_sample_sharding_is_world_size_invariant():
+    """SURVEY 8(e), DSVI row: S likelihood samples split over 2 and 4 emulated ranks; the summed loss and gradients must
+    equal the single-rank step (same Philox draws by global element index)."""
+    from nonstationary_precip_b200.models import dgps
+    torch.manual_seed(11)
+    g = torch.Generator().manual_seed(11)
+    B, S = 96, 8
+    x = (torch.rand(B, 2, generator=g, dtype=torch.float64) * 2 - 1).cuda()  # tied hidden layers need d_in = 2 (= width)
+    y = torch.sin(3 * x[:, 0]).contiguous()
+    model = dgps.DeepGP(2, x.shape, num_inducing=24).cuda().double()
+    mll = dgps.DeepApproximateMLL(dgps.VariationalELBO(model.likelihood, model, 1000))
+
+    def step(rank, world):
+        for p in model.parameters():
+            p.grad = None
+        with dgps.num_likelihood_samples(S), dgps.sample_shard(rank, world):
+            out = model(x, seed=77)
+            assert out.mean.shape[0] == S // world
+            loss = -mll(out, y)
+        loss.backward()
+        return loss.detach(), torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+
+    l1, g1 = step(0, 1)
+    for world in (2, 4):
+        parts = [step(r, world) for r in range(world)]
+        lw, gw = sum(p[0] for p in parts), sum(p[1] for p in parts)
+        assert abs(lw.item() - l1.item()) < 1e-12 * abs(l1.item())
+        assert (gw - g1).abs().max().item() < 1e-11 * g1.abs().max().item()
+    with pytest.raises(ValueError):
+        step(0, 3)
+    # the flat-buffer gradient all-reduce helper (identity "collective": x2)
+    step(0, 1)
+    n = dgps.allreduce_gradients(model, lambda t: t.mul_(2.0))
+    assert n == g1.numel()
+    assert torch.allclose(torch.cat([p.grad.reshape(-1) for p in model.parameters()]), 2.0 * g1)
