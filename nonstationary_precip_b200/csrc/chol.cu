@@ -143,9 +143,13 @@ __device__ __forceinline__ void acc_axpy_global(const double (&acc)[2][4][2], do
 // per thread, the trailing update one element per thread.  The inverse is then assembled by recursive doubling
 // (8 -> 16 -> 32 -> 64) with element-per-thread products.  tmp: >= 32*32 doubles.
 // ---------------------------------------------------------------------------------------------------------------------
+// The critical path of the whole factorisation is the chain of 64 dependent pivots of each diagonal block, so the
+// elimination below keeps the square root OFF that chain: the Schur complement is updated with the unnormalised column
+// and the reciprocal pivot (a_ik -= (a_ij / d_j) a_kj: reciprocal + multiply + fma per pivot), while 1/sqrt(d_j), which
+// only normalises the stored column, is computed on the side.
 __device__ __forceinline__ void chol8_serial(double* s, double* sInv, int c0, int global_offset,
                                              int* __restrict__ info) {
-  double a[8][8], inv[8];
+  double a[8][8], isq[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
 #pragma unroll
@@ -154,20 +158,20 @@ __device__ __forceinline__ void chol8_serial(double* s, double* sInv, int c0, in
   for (int j = 0; j < 8; ++j) {
     const double dj = a[j][j];
     if (!(dj > 0.0)) atomicCAS(info, 0, global_offset + c0 + j + 1);
-    inv[j] = rsqrt(dj);
-    a[j][j] = dj * inv[j];
+    const double rj = __drcp_rn(dj);
+    isq[j] = rsqrt(dj);
 #pragma unroll
-    for (int i = j + 1; i < 8; ++i) a[i][j] *= inv[j];
+    for (int i = j + 1; i < 8; ++i) {
+      const double t = a[i][j] * rj;
 #pragma unroll
-    for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-      for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-a[i][j], a[k][j], a[i][k]);
+      for (int k = j + 1; k <= i; ++k) a[i][k] = fma(-t, a[k][j], a[i][k]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
-    sInv[c0 + r] = inv[r];
+    sInv[c0 + r] = isq[r];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s[(c0 + r) * TLD + c0 + c] = (c <= r) ? a[r][c] : 0.0;
+    for (int c = 0; c < 8; ++c) s[(c0 + r) * TLD + c0 + c] = (c <= r) ? a[r][c] * isq[c] : 0.0;
   }
 }
 
@@ -185,29 +189,39 @@ __device__ __forceinline__ void inv8_column(const double* s, const double* sInv,
   for (int r = 0; r < 8; ++r) x[(c0 + r) * TLD + c0 + c] = xc[r];
 }
 
+// rank-8 update of one 8x8 tile on the tensor pipe: s[ri.., ck..] -= Lr Lc^T with Lr = s[ri.., c0..c0+7], Lc = s[ck.., c0..c0+7]
+__device__ __forceinline__ void rank8_tile_update(double* s, int ri, int ck, int c0, int g, int t4) {
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 8; kk += 4)
+    dmma884(acc0, acc1, s[(ri + g) * TLD + c0 + kk + t4], s[(ck + g) * TLD + c0 + kk + t4]);
+  double* q = s + (ri + g) * TLD + ck + 2 * t4;
+  q[0] -= acc0;
+  q[1] -= acc1;
+}
+
 __device__ void factor_invert_64(double* s, double* x, double* tmp, int global_offset, int* __restrict__ info) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  constexpr int NWARP = CT / 32;
   double* sInv = tmp + 32 * 32;  // 64 reciprocal pivots (tmp holds >= 64*68 doubles)
   for (int e = tid; e < TB * TB; e += CT) x[(e >> 6) * TLD + (e & 63)] = 0.0;
+  if (tid == 0) chol8_serial(s, sInv, 0, global_offset, info);
   __syncthreads();
+  // Two barriers per 8 columns.  Phase A: panel rows by forward substitution against the 8x8 pivot factor, one row per
+  // thread.  Phase B: rank-8 trailing update, one 8x8 tile per warp and DMMA pair; warp 0 takes the NEXT pivot tile first
+  // and one of its threads factors it at once (look-ahead), so the serial 8-pivot chain (the critical path: 64
+  // dependent rsqrt's) runs under the other warps' tiles and under the inversion of the current pivot block (warp 7).
   for (int c0 = 0; c0 < TB; c0 += 8) {
-    if (tid == 0) chol8_serial(s, sInv, c0, global_offset, info);
-    __syncthreads();
-    if (tid < 8) inv8_column(s, sInv, x, c0, tid);
-    __syncthreads();
-    const int r1 = c0 + 8, n = TB - r1;
-    // panel: row r of L[:, c0:c0+8] = A[r, c0:c0+8] * X8^T  (X8 lower: X8[c][k], k <= c)
+    const int r1 = c0 + 8, n = TB - r1, nt = n >> 3;
     if (tid < n) {
       const int r = r1 + tid;
-      double a[8], l[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = s[r * TLD + c0 + k];
+      double l[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        double acc = 0.0;
+        double acc = s[r * TLD + c0 + c];
 #pragma unroll
-        for (int k = 0; k <= c; ++k) acc = fma(a[k], x[(c0 + c) * TLD + c0 + k], acc);
-        l[c] = acc;
+        for (int k = 0; k < c; ++k) acc = fma(-l[k], s[(c0 + c) * TLD + c0 + k], acc);
+        l[c] = acc * sInv[c0 + c];
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -216,35 +230,51 @@ __device__ void factor_invert_64(double* s, double* x, double* tmp, int global_o
       }
     }
     __syncthreads();
-    // trailing update of the lower triangle: s[i][k] -= sum_c s[i][c0+c] * s[k][c0+c],  r1 <= k <= i < 64
-    for (int e = tid; e < n * n; e += CT) {
-      const int i = r1 + e / n, k = r1 + e % n;
-      if (k <= i) {
-        double acc = s[i * TLD + k];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc = fma(-s[i * TLD + c0 + c], s[k * TLD + c0 + c], acc);
-        s[i * TLD + k] = acc;
+    if (warp == 0) {
+      if (nt > 0) {
+        rank8_tile_update(s, r1, r1, c0, g, t4);
+        __syncwarp();
+        if (lane == 0) chol8_serial(s, sInv, r1, global_offset, info);
+      }
+    } else {
+      if (warp == NWARP - 1 && lane < 8) inv8_column(s, sInv, x, c0, lane);
+      __syncwarp();
+      // lower-triangular tiles (ti >= tk) of the trailing block except (0,0), round-robin over warps 1..NWARP-1
+      const int ntiles = nt * (nt + 1) / 2;
+      for (int e = warp; e < ntiles; e += NWARP - 1) {
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        const int tk = e - ti * (ti + 1) / 2;
+        rank8_tile_update(s, r1 + 8 * ti, r1 + 8 * tk, c0, g, t4);
       }
     }
     __syncthreads();
   }
-  // inverse by doubling: for block pairs (size sz): T = L21 X11;  X21 = -X22 T
+  // inverse by doubling on the tensor pipe: for block pairs of size sz, T = L21 X11, then X21 = -X22 T (8x8 output
+  // tiles round-robin over the warps; structurally zero k-ranges skipped)
   for (int sz = 8; sz < TB; sz *= 2) {
-    const int pairs = TB / (2 * sz);
-    for (int e = tid; e < pairs * sz * sz; e += CT) {
-      const int pr = e / (sz * sz), q = e % (sz * sz), r = q / sz, c = q % sz;
+    const int tps = sz >> 3, tiles = (TB / (2 * sz)) * tps * tps;
+    for (int e = warp; e < tiles; e += NWARP) {
+      const int pr = e / (tps * tps), q = e % (tps * tps), tr = q / tps, tc = q % tps;
       const int b0 = pr * 2 * sz;
-      double acc = 0.0;
-      for (int k = c; k < sz; ++k) acc = fma(s[(b0 + sz + r) * TLD + b0 + k], x[(b0 + k) * TLD + b0 + c], acc);
-      tmp[e] = acc;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int kk = 8 * tc; kk < sz; kk += 4)
+        dmma884(acc0, acc1, s[(b0 + sz + 8 * tr + g) * TLD + b0 + kk + t4], x[(b0 + kk + t4) * TLD + b0 + 8 * tc + g]);
+      double* q2 = tmp + pr * sz * sz + (8 * tr + g) * sz + 8 * tc + 2 * t4;
+      q2[0] = acc0;
+      q2[1] = acc1;
     }
     __syncthreads();
-    for (int e = tid; e < pairs * sz * sz; e += CT) {
-      const int pr = e / (sz * sz), q = e % (sz * sz), r = q / sz, c = q % sz;
+    for (int e = warp; e < tiles; e += NWARP) {
+      const int pr = e / (tps * tps), q = e % (tps * tps), tr = q / tps, tc = q % tps;
       const int b0 = pr * 2 * sz;
-      double acc = 0.0;
-      for (int k = 0; k <= r; ++k) acc = fma(x[(b0 + sz + r) * TLD + b0 + sz + k], tmp[pr * sz * sz + k * sz + c], acc);
-      x[(b0 + sz + r) * TLD + b0 + c] = -acc;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int kk = 0; kk < 8 * (tr + 1); kk += 4)
+        dmma884(acc0, acc1, x[(b0 + sz + 8 * tr + g) * TLD + b0 + sz + kk + t4],
+                tmp[pr * sz * sz + (kk + t4) * sz + 8 * tc + g]);
+      double* q2 = x + (b0 + sz + 8 * tr + g) * TLD + b0 + 8 * tc + 2 * t4;
+      q2[0] = -acc0;
+      q2[1] = -acc1;
     }
     __syncthreads();
   }
@@ -383,6 +413,9 @@ __global__ void zero_matrix_kernel(int M, double* __restrict__ D, long ldd) {
   D[(long)(idx / M) * ldd + (idx % M)] = 0.0;
 }
 
+int dgemm_impl(int transA, int transB, int M, int N, int K, double alpha, const double* A, long lda, const double* B,
+               long ldb, double beta, double* C, long ldc, int tri_a, int tri_b, int out_tri, cudaStream_t st);  // dgemm.cu
+
 constexpr int FIRST_SMEM = 3 * TILE_SMEM * (int)sizeof(double);
 constexpr int STEP_SMEM = 3 * TILE_SMEM * (int)sizeof(double);
 constexpr int LEVEL_SMEM = 2 * TILE_SMEM * (int)sizeof(double);
@@ -418,6 +451,22 @@ int potrf_inv_impl(int M, double* A, long lda, double* P, long ldp, double* work
   }
   for (int b = TB; b < M; b *= 2) {
     const int pairs = (M + 2 * b - 1) / (2 * b);
+    if (b >= 256) {
+      // large blocks: the pipelined (cp.async, split-K) DMMA GEMM of dgemm.cu, one call per block pair and phase
+      for (int pr = 0; pr < pairs; ++pr) {
+        const int s0 = pr * 2 * b, r1 = s0 + b;
+        if (r1 >= M) continue;
+        const int b2 = min(b, M - r1);
+        double* Tp = T + (long)pr * b * b;
+        int rc = dgemm_impl(0, 0, b2, b, b, 1.0, L + (long)r1 * ldl + s0, ldl, P + (long)s0 * ldp + s0, ldp, 0.0, Tp, b,
+                            0, 1, 0, st);
+        if (rc != NPGP_OK) return rc;
+        rc = dgemm_impl(0, 0, b2, b, b2, -1.0, P + (long)r1 * ldp + r1, ldp, Tp, b, 0.0, P + (long)r1 * ldp + s0, ldp,
+                        1, 0, 0, st);
+        if (rc != NPGP_OK) return rc;
+      }
+      continue;
+    }
     dim3 grid(b / TB, b / TB, pairs);
     trinv_level_kernel<<<grid, CT, LEVEL_SMEM, st>>>(M, b, 0, L, ldl, P, ldp, T);
     NPGP_LAUNCH_CHECK();

@@ -362,7 +362,7 @@ int dgemm_impl(int transA, int transB, int M, int N, int K, double alpha, const 
   p.alpha = alpha; p.beta = beta; p.tri_a = tri_a; p.tri_b = tri_b; p.out_tri = out_tri; p.splits = 1;
   // small outputs with a long K: split K so that the 148 SMs have work
   const long tiles = (long)ceil_div(M, tile_bm()) * ceil_div(N, tile_bn());
-  if (tiles * 2 <= kNumSMs * ctas_per_sm() && K >= 8 * kMaxBK * 4) {
+  if (tiles * 2 <= kNumSMs * ctas_per_sm() && K >= 8 * kMaxBK * 2) {
     int s = (int)(kNumSMs * ctas_per_sm() / tiles);
     s = min(s, K / (8 * kMaxBK));
     s = min(s, 16);
