@@ -114,6 +114,7 @@ class SVGPGibbs:
         self.step_count = 0
         self.step_dev = torch.zeros(1, **f64)  # Adam step counter on the device
         self._side = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
+        self._side2 = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self.overlap = True
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
@@ -186,6 +187,18 @@ class SVGPGibbs:
         if self._side is not None and self.overlap:
             torch.cuda.current_stream().wait_stream(self._side)
 
+    def _fork2(self):
+        """Second side stream, forked from whatever stream is current: for M x M GEMMs that are independent of the
+        latency-bound chain running on the current stream (the GEMM fills the SMs the chain leaves idle)."""
+        if self._side2 is None or not self.overlap:
+            return contextlib.nullcontext()
+        self._side2.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side2)
+
+    def _join2(self):
+        if self._side2 is not None and self.overlap:
+            torch.cuda.current_stream().wait_stream(self._side2)
+
     def _field_prepare(self, fz):
         """Z-side part of the field interpolation (independent of the rows): the prior-kernel factorisations at Z and
         the interpolation weights (alpha for the log-normal field, W = (K_row + 1e-5 I)^-1 H for the matrix field)."""
@@ -232,12 +245,14 @@ class SVGPGibbs:
 
     def _zz_forward(self, fz, s):
         o, p, M = self.o, self.p, self.M
+        Ls = torch.tril(p["Ls"])
+        with self._fork2():  # S - I does not depend on the factorisation: under the (latency-bound) Cholesky
+            E = o.dgemm(Ls, Ls, transB=True, tri_a=1, tri_b=2) - self.eye
         Kzz = self._kernel_fwd(p["Z"], fz, p["Z"], fz, s)
         Kzz.diagonal().add_(self.jitter_zz)
         L, P, info = o.potrf_inv(Kzz, overwrite=True)
-        Ls = torch.tril(p["Ls"])
         u = o.colwsum(P, w=p["m"])  # P^T m
-        E = o.dgemm(Ls, Ls, transB=True, tri_a=1, tri_b=2) - self.eye
+        self._join2()
         EP = o.dgemm(E, P, tri_b=1)
         C = o.dgemm(P, EP, transA=True, tri_a=2)
         return dict(L=L, P=P, info=info, Ls=Ls, u=u, E=E, C=C)
@@ -301,16 +316,18 @@ class SVGPGibbs:
             with self._sec("m3_bwd+kzz_bwd"):
                 dm = o.gemv_n(P, du)
                 dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
+                with self._fork2():  # dL_s branch, independent of the dKzz chain below
+                    dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
+                    g["m"].copy_(-(dm - rep * m / self.N))
+                    g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
                 X = o.dgemm(E, dE, alpha=2.0)
                 X.addr_(m, dm)
                 o.phi_mask_(X, -1.0)
                 dK = o.dgemm(o.dgemm(P, X, transA=True, tri_a=2, tri_b=1), P, tri_b=1)
                 dKzz = 0.5 * (dK + dK.T)
-                dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
-                g["m"].copy_(-(dm - rep * m / self.N))
-                g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
                 dfz1, dfz2, dZ1, dZ2, ds2 = self._kernel_bwd(Z, fz, Z, fz, s, G=dKzz, need_dx1=self.learn_z,
                                                              need_dx2=self.learn_z, need_dscale=True)
+                self._join2()
         if wsyrk_done is not None:
             torch.cuda.current_stream().wait_event(wsyrk_done)
         with self._sec("kxz_bwd"):
