@@ -7,6 +7,10 @@
 #include "../../nonstationary_precip_b200/csrc/chol.cu"
 
 long npgp_launch_counter = 0;  // normally defined in capi.cu
+namespace npgp {  // normally dgemm.cu (the probe never takes the path that calls it)
+int dgemm_impl(int, int, int, int, int, double, const double*, long, const double*, long, double, double*, long, int, int,
+               int, cudaStream_t) { return -2; }
+}
 
 using namespace npgp;
 
@@ -91,6 +95,48 @@ int main() {
     printf("rep %d:", rep);
     for (int k = 1; k <= 7; ++k) printf("  %s=%lld", names[k - 1], hs[k] - hs[k - 1]);
     printf("  (cycles)\n");
+  }
+  // back-to-back launches of one panel step (M = 1024): j = 0 (120 CTAs) and j = 14 (the diagonal CTA alone)
+  {
+    const int M = 1024, nblk = 16;
+    double *Am, *Lm, *Pm;
+    int* info;
+    cudaMalloc(&Am, sizeof(double) * M * M);
+    cudaMalloc(&Lm, sizeof(double) * M * M);
+    cudaMalloc(&Pm, sizeof(double) * M * M);
+    cudaMalloc(&info, sizeof(int));
+    std::vector<double> hm((size_t)M * M);
+    for (int i = 0; i < M; ++i)
+      for (int j = 0; j < M; ++j) hm[(size_t)i * M + j] = (i == j ? 4.0 : 0.0) + 1.0 / (1.0 + (i > j ? i - j : j - i));
+    cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM);
+    cudaFuncSetAttribute(potrf_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int js[2] = {0, 14};
+    for (int v = 0; v < 2; ++v) {
+      const int j = js[v], r = nblk - 1 - j, reps = 50;
+      cudaMemcpy(Am, hm.data(), sizeof(double) * M * M, cudaMemcpyHostToDevice);
+      cudaMemset(Pm, 0, sizeof(double) * M * M);
+      cudaMemset(info, 0, sizeof(int));
+      potrf_first_kernel<<<1, CT, FIRST_SMEM>>>(M, Am, M, Lm, M, Pm, M, info);
+      for (int w = 0; w < 3; ++w) potrf_step_kernel<<<r * (r + 1) / 2, CT, STEP_SMEM>>>(M, nblk, j, Am, M, Lm, M, Pm, M, info);
+      cudaEventRecord(e0);
+      for (int w = 0; w < reps; ++w)
+        potrf_step_kernel<<<r * (r + 1) / 2, CT, STEP_SMEM>>>(M, nblk, j, Am, M, Lm, M, Pm, M, info);
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      printf("potrf_step_kernel j=%d (%d CTAs): %.2f us per launch, back to back\n", j, r * (r + 1) / 2, 1e3 * ms / reps);
+    }
+    cudaEventRecord(e0);
+    for (int w = 0; w < 50; ++w) potrf_first_kernel<<<1, CT, FIRST_SMEM>>>(M, Am, M, Lm, M, Pm, M, info);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("potrf_first_kernel: %.2f us per launch\n", 1e3 * ms / 50);
   }
   return 0;
 }
