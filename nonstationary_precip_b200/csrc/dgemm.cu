@@ -151,9 +151,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, MINB) dgemm_kernel(GemmParams p)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
-  // weights known (on the device) to be all equal: fold them into the epilogue
-  const bool w_uniform = HAS_W && p.w_uniform_count && (*p.w_uniform_count == p.w_uniform_target);
-  const double alpha_eff = w_uniform ? p.alpha * p.w[0] : p.alpha;
+  // Device-side weight hint: the launcher enqueues BOTH instantiations; the unweighted one runs when the flag says that
+  // all weights are equal (w[0] folded into the epilogue), the weighted one otherwise; the other exits here.
+  constexpr bool w_uniform = false;
+  double alpha_eff = p.alpha;
+  if (p.w_uniform_count) {
+    const bool uni = (*p.w_uniform_count == p.w_uniform_target);
+    if (HAS_W ? uni : !uni) return;
+    if (!HAS_W) alpha_eff *= p.w[0];
+  }
 
   double acc[MT][NT][2];
 #pragma unroll
@@ -314,8 +320,15 @@ static int launch_cfg(const GemmParams& p, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(ceil_div(p.N, Cfg::BN), ceil_div(p.M, Cfg::BM), p.splits);
-  if (p.w) kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
-  else kern<<<grid, GEMM_THREADS, smem, st>>>(p);
+  if (p.w && p.w_uniform_count) {
+    kern<<<grid, GEMM_THREADS, smem, st>>>(p);
+    NPGP_LAUNCH_CHECK();
+    kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
+  } else if (p.w) {
+    kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
+  } else {
+    kern<<<grid, GEMM_THREADS, smem, st>>>(p);
+  }
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
@@ -430,9 +443,20 @@ static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, con
   p.alpha = alpha; p.beta = 0.0; p.out_tri = 2; p.w = w;
   p.w_uniform_count = w ? w_uniform_count : nullptr; p.w_uniform_target = w_uniform_target;
   const long tiles = ((long)ceil_div(M, tile_bm()) * ceil_div(M, tile_bn()) + ceil_div(M, tile_bm())) / 2;
-  int s = (int)max(1L, (long)(kNumSMs * ctas_per_sm()) / tiles);
-  s = min(s, max(1, n / (16 * kMaxBK)));
-  p.splits = max(1, min(s, 32));
+  // split the row range so that tiles x splits fills whole waves of resident CTAs: the cost of a choice is
+  // (number of waves) / splits; take the cheapest among 1..32 splits of at least 512 rows each
+  const long slots = (long)kNumSMs * ctas_per_sm();
+  const int smax = (int)max(1L, min(32L, (long)n / (16 * kMaxBK)));
+  int best_s = 1;
+  double best_cost = 1e300;
+  for (int sp = 1; sp <= smax; ++sp) {
+    const double cost = (double)((tiles * sp + slots - 1) / slots) / sp;
+    if (cost < best_cost * (1.0 - 1e-3)) {  // prefer fewer splits (less atomic traffic) on ties
+      best_cost = cost;
+      best_s = sp;
+    }
+  }
+  p.splits = best_s;
   if (p.splits > 1) {
     const long tot = (long)M * M;
     scale_matrix_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(M, M, Out, ldo, 0.0, 0);
