@@ -22,9 +22,21 @@
 
 namespace npgp {
 
+// 1/sqrt(x) and 1/x for the tile kernels: hardware seed (MUFU.RSQ64H / MUFU.RCP64H, ~20 bits) + two Newton steps, branch
+// free.  The library versions carry special-case paths (BSSY/CALL around every use) that cost ~30 % of the tile kernels'
+// issue slots; the arguments here (products of squared lengthscales, determinants of positive definite 2x2 / 3x3
+// matrices) are positive normal numbers, anything else ends in NaN/inf exactly as a failed factorisation would.
 NPGP_HD double fast_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+  }
+  return y;
 #else
   return 1.0 / sqrt(x);
 #endif
@@ -59,7 +71,14 @@ NPGP_HD double exp_neg(double x, const double* tab) {
 
 NPGP_HD double fast_rcp(double x) {
 #if defined(__CUDA_ARCH__)
-  return __drcp_rn(x);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+  }
+  return r;
 #else
   return 1.0 / x;
 #endif
