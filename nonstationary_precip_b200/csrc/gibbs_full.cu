@@ -108,8 +108,11 @@ __global__ void __launch_bounds__(kNT) gibbs_full_fwd_kernel(int n1, int n2, con
 }
 
 
+#ifndef NPGP_FULL_BWD_MINB
+#define NPGP_FULL_BWD_MINB 2
+#endif
 template <int d, bool DX1, bool DX2, int CPT>
-__global__ void __launch_bounds__(kNT) gibbs_full_bwd_kernel(int n1, int n2, const double* __restrict__ x1,
+__global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel(int n1, int n2, const double* __restrict__ x1,
                                                              const double* __restrict__ S1,
                                                              const double* __restrict__ x2,
                                                              const double* __restrict__ S2, double jit2,

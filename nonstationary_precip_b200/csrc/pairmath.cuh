@@ -51,7 +51,7 @@ __host__ __device__
 // exp per pair.  `tab` is the 256-entry table of 2^(j/256) (in shared memory on the device).
 NPGP_HD double exp_neg(double x, const double* tab) {
 #if defined(__CUDA_ARCH__)
-  if (x < -708.0) return 0.0;
+  x = fmax(x, -708.0);  // branch free: exp(-708) = 3e-308 stands in for the underflowed tail
   const double t = fma(x, kInvLn2x256, 6755399441055744.0);  // 2^52 + 2^51: the integer lands in the low mantissa bits
   const int n = __double2loint(t);
   const double nd = t - 6755399441055744.0;
