@@ -14,6 +14,7 @@
 // [16][cols+4], whichever matches the operand's global layout; with a leading dimension = 4 (mod 16) doubles both
 // fragment-load patterns are bank-conflict free for 64-bit accesses.  Chunk addresses are computed once per CTA; the
 // per-stage producer work is a pointer bump (plus a byte count at ragged edges).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace npgp {
@@ -373,10 +374,13 @@ int dgemm_impl(int transA, int transB, int M, int N, int K, double alpha, const 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.alpha = alpha; p.beta = beta; p.tri_a = tri_a; p.tri_b = tri_b; p.out_tri = out_tri; p.splits = 1;
-  // small outputs with a long K: split K so that the 148 SMs have work
+  // small outputs with a long K: split K so that the 148 SMs have work.  At least 4 splits when the tiles alone do not
+  // fill the resident-CTA slots: measured on the nine M = 1024 GEMMs of the SVGP O(M^3) chain (tools/bench_tri_gemm.py),
+  // 2 splits (512 CTAs on 444 slots: 1.15 waves) cost 0.100 ms for the dense product against 0.075 ms with 4, and the
+  // triangular ones gain 5-20 % because the k-range of each tile is split, which evens out their unequal lengths.
   const long tiles = (long)ceil_div(M, tile_bm()) * ceil_div(N, tile_bn());
   if (tiles * 2 <= kNumSMs * ctas_per_sm() && K >= 8 * kMaxBK * 2) {
-    int s = (int)(kNumSMs * ctas_per_sm() / tiles);
+    int s = (int)max(4L, kNumSMs * ctas_per_sm() / tiles);
     s = min(s, K / (8 * kMaxBK));
     s = min(s, 16);
     if (s > 1) p.splits = s;
