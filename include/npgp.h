@@ -152,6 +152,15 @@ int npgp_rbfper_fwd(int n1, int n2, const double* t1, const double* t2, const do
 int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const double* hyp, const double* G, long ldg,
                     double* out4, double* dt2, npgp_stream_t stream);
 
+/* Row-quadratic contraction on the integer tensor cores (tcgen05.mma kind::i8 + TMEM), exact Ozaki split of both
+ * operands into 8 signed 7-bit slices (csrc/ozaki.cu): same contract as npgp_rowquad, C symmetric, M % 64 == 0, T 16-byte
+ * aligned with even ldt.  work: npgp_rowquad_i8_workspace_bytes(n, M) bytes of device memory (slices + exponents).
+ * Replaces the same reference lines as npgp_rowquad (k_ux1.matmul(...), models/gibbs_kernels.py:222-232; A^T (S - I) A of
+ * the whitened SVGP). */
+long npgp_rowquad_i8_workspace_bytes(int n, int M);
+int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
+                    void* work, long work_bytes, npgp_stream_t stream);
+
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 

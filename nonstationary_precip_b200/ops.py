@@ -164,6 +164,26 @@ def rowquad(K, Cm, need_q=True, T=None):
     return T, q
 
 
+_I8_WORK = {}
+
+
+def rowquad_i8(K, Cm, need_q=True, T=None):
+    """rowquad on the integer tensor cores (tcgen05 kind::i8, exact Ozaki split, see csrc/ozaki.cu).  Cm must be
+    symmetric and M a multiple of 64.  The slice workspace is cached per (device, n, M)."""
+    n, M = K.shape
+    if T is None:
+        T = torch.empty(n, M, dtype=torch.float64, device=K.device)
+    q = torch.zeros(n, dtype=torch.float64, device=K.device) if need_q else None
+    nbytes = lib().npgp_rowquad_i8_workspace_bytes(n, M)
+    key = (K.device.index, n, M)
+    work = _I8_WORK.get(key)
+    if work is None:
+        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
+    check(lib().npgp_rowquad_i8(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q), ptr(work),
+                                nbytes, stream()), "npgp_rowquad_i8")
+    return T, q
+
+
 def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0):
     """alpha * K^T diag(w) K (symmetric M x M).  uniform_count (device scalar) == uniform_target tells the kernel, on
     the device, that all weights are equal."""
