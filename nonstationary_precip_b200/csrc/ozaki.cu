@@ -27,7 +27,8 @@ constexpr int OZ_NS = 8;          // slices per operand
 constexpr int OZ_BM = 128;        // rows of K per tile (TMEM lanes)
 constexpr int OZ_BN = 64;         // columns per tile (TMEM columns per accumulator)
 constexpr int OZ_KS = 32;         // bytes of K per pipeline stage = one MMA k-step
-constexpr int OZ_STAGES = 4;
+constexpr int OZ_STAGES = 3;
+constexpr int OZ_KLD = OZ_BN + 2;     // leading dimension (doubles) of the staged K tile: conflict-free 16-byte row reads
 constexpr int OZ_A_STAGE = OZ_NS * OZ_BM * OZ_KS;   // 32 KB
 constexpr int OZ_B_STAGE = OZ_NS * OZ_BN * OZ_KS;   // 16 KB
 constexpr int OZ_THREADS = 192;
@@ -38,30 +39,85 @@ constexpr int OZ_THREADS = 192;
 //   byte offset = ((((r / BR) * nks + k / 32) * 8 + p) * 2 + (k % 32) / 16) * (BR * 16) + ((r % BR) / 8) * 128 + (r % 8) * 16 + k % 16
 // expo[r]: x = X[r, :] * 2^-expo[r] in [-1, 1]
 // ---------------------------------------------------------------------------------------------------------------------
+// CTA = 8 consecutive rows x 64 chunks of 16 columns (512 threads, Kd <= 1024 per pass; longer rows loop): thread
+// (row = t % 8, chunk = t / 8) keeps its 16 values in registers, the row maximum is reduced through shuffles + shared
+// memory, and every slice is written as ONE 16-byte vector; the 8 lanes of a row group write 128 contiguous bytes (one
+// core matrix).
 template <int BR>
-__global__ void __launch_bounds__(256) oz_slice_kernel(int R, int Rpad, int Kd, const double* __restrict__ X, long ldx,
+__global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, const double* __restrict__ X, long ldx,
                                                        int8_t* __restrict__ out, int* __restrict__ expo) {
-  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Rpad) return;
-  const int r = warp, nks = Kd / OZ_KS;
+  __shared__ double smax[16][8];
+  __shared__ int sexp[8];
+  const int t = threadIdx.x, rr = t & 7, ch = t >> 3, warp = t >> 5;
+  const int r = blockIdx.x * 8 + rr;
+  const int nks = Kd / OZ_KS, nch = Kd / 16;
+  // pass 1: row maximum (values of the first 64 chunks stay in registers)
+  double v[16];
   double mx = 0.0;
-  if (r < R)
-    for (int k = lane; k < Kd; k += 32) mx = fmax(mx, fabs(X[(long)r * ldx + k]));
+  for (int c = ch; c < nch; c += 64) {
+    if (r < R) {
+      const double2* src = reinterpret_cast<const double2*>(X + (long)r * ldx + c * 16);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  int e = 0;
-  if (mx > 0.0) frexp(mx, &e);  // mx = m 2^e, m in [0.5, 1)  =>  |x| 2^-e < 1
-  if (lane == 0) expo[r] = e;
+      for (int j = 0; j < 8; ++j) {
+        const double2 d = src[j];
+        if (c == ch) { v[2 * j] = d.x; v[2 * j + 1] = d.y; }
+        mx = fmax(mx, fmax(fabs(d.x), fabs(d.y)));
+      }
+    } else if (c == ch) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.0;
+    }
+  }
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  if ((t & 31) < 8) smax[warp][rr] = mx;
+  __syncthreads();
+  if (t < 8) {
+    double m = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) m = fmax(m, smax[w][t]);
+    int e = 0;
+    if (m > 0.0) frexp(m, &e);  // m = f 2^e, f in [0.5, 1)  =>  |x| 2^-e < 1
+    sexp[t] = e;
+    if (blockIdx.x * 8 + t < Rpad) expo[blockIdx.x * 8 + t] = e;
+  }
+  __syncthreads();
+  if (r >= Rpad) return;
+  const int e = sexp[rr];
+  const double sc = __hiloint2double((1023 + 6 - e) << 20, 0);  // 2^(6 - e)
   const long blk = (long)(r / BR) * nks;
   const int rin = ((r % BR) / 8) * 128 + (r % 8) * 16;
-  for (int k = lane; k < Kd; k += 32) {
-    double x = (r < R) ? ldexp(X[(long)r * ldx + k], 6 - e) : 0.0;  // x 2^6, in [-64, 64]
-    int8_t* base = out + ((blk + k / OZ_KS) * OZ_NS * 2 + (k % OZ_KS) / 16) * (long)(BR * 16) + rin + (k % 16);
+  for (int c = ch; c < nch; c += 64) {
+    if (c != ch) {
+      if (r < R) {
+        const double2* src = reinterpret_cast<const double2*>(X + (long)r * ldx + c * 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double2 d = src[j];
+          v[2 * j] = d.x;
+          v[2 * j + 1] = d.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= sc;  // x 2^6, in (-64, 64); exact
+    int8_t* base = out + ((blk + c / 2) * OZ_NS * 2 + (c & 1)) * (long)(BR * 16) + rin;
 #pragma unroll
     for (int p = 0; p < OZ_NS; ++p) {
-      const double a = rint(x);
-      base[(long)p * 2 * (BR * 16)] = (int8_t)(int)a;
-      x = (x - a) * 128.0;  // exact: removes the leading 7 bits of the remainder
+      uint32_t w[4];
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) {
+          const int j = g4 * 4 + b4;
+          const double a = rint(v[j]);
+          word |= ((uint32_t)(int)a & 0xffu) << (8 * b4);
+          v[j] = (v[j] - a) * 128.0;  // exact: removes the leading 7 bits of the remainder
+        }
+        w[g4] = word;
+      }
+      *reinterpret_cast<uint4*>(base + (long)p * 2 * (BR * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
@@ -123,10 +179,12 @@ __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int* __restrict__ ea,
                   const int8_t* __restrict__ Bs, const int* __restrict__ eb, const double* __restrict__ Kmat, long ldk,
-                  double* __restrict__ T, long ldt, double* __restrict__ q) {
+                  double* __restrict__ T, long ldt, double* __restrict__ q, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t oz_sm[];
   uint8_t* sA = oz_sm;                                   // OZ_STAGES x 32 KB
   uint8_t* sB = oz_sm + OZ_STAGES * OZ_A_STAGE;          // OZ_STAGES x 16 KB
+  double* sK = reinterpret_cast<double*>(oz_sm + OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE));  // 128 x OZ_KLD tile of K
+  __shared__ double scol[OZ_BN];                         // 2^f_j of the tile's columns
   __shared__ __align__(8) uint64_t full[OZ_STAGES], empty[OZ_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,18 +214,22 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int rb = tile / n_cb, cb = tile % n_cb;
         const int8_t* a = As + (long)rb * nks * OZ_A_STAGE;
         const int8_t* b = Bs + (long)cb * nks * OZ_B_STAGE;
         for (int ks = 0; ks < nks; ++ks) {
+          const long long c0 = dbg ? clock64() : 0;
           oz_mbar_wait(&empty[stage], phase ^ 1);
+          if (dbg) w_empty += clock64() - c0;
           oz_mbar_expect_tx(&full[stage], OZ_A_STAGE + OZ_B_STAGE);
           oz_bulk_g2s(sA + stage * OZ_A_STAGE, a + (long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
           oz_bulk_g2s(sB + stage * OZ_B_STAGE, b + (long)ks * OZ_B_STAGE, OZ_B_STAGE, &full[stage]);
           if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg && blockIdx.x == 0) dbg[0] = w_empty;
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -176,11 +238,16 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
+      long long w_acc = 0, w_full = 0, t_all = dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        long long c0 = dbg ? clock64() : 0;
         oz_mbar_wait(&acc_empty, acc_phase ^ 1);  // epilogue has drained the accumulators of the previous tile
+        if (dbg) w_acc += clock64() - c0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int ks = 0; ks < nks; ++ks) {
+          c0 = dbg ? clock64() : 0;
           oz_mbar_wait(&full[stage], phase);
+          if (dbg) w_full += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = oz_smem(sA + stage * OZ_A_STAGE), b0 = oz_smem(sB + stage * OZ_B_STAGE);
 #pragma unroll
@@ -200,41 +267,69 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
         oz_commit(&acc_full);
         acc_phase ^= 1;
       }
+      if (dbg && blockIdx.x == 0) {
+        dbg[1] = w_acc;
+        dbg[2] = w_full;
+        dbg[3] = clock64() - t_all;
+      }
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
+    const int quad = warp & 3, et = tid - 64;  // et: 0..127
     uint32_t acc_phase = 0;
+    long long w_accfull = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int rb = tile / n_cb, cb = tile % n_cb;
       const int row = rb * OZ_BM + quad * 32 + lane;
+      // while the MMAs of this tile run: stage the K tile (row dot) and the column scales
+      if (q) {
+        for (int rr = et >> 5; rr < OZ_BM; rr += 4) {  // one row (512 contiguous bytes) per warp instruction
+          const int gr = rb * OZ_BM + rr;
+          double2 d = make_double2(0.0, 0.0);
+          if (gr < n) d = *reinterpret_cast<const double2*>(Kmat + (long)gr * ldk + cb * OZ_BN + 2 * lane);
+          *reinterpret_cast<double2*>(sK + rr * OZ_KLD + 2 * lane) = d;
+        }
+      }
+      if (et < OZ_BN) scol[et] = __hiloint2double((1023 + eb[cb * OZ_BN + et]) << 20, 0);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long c0 = dbg ? clock64() : 0;
       oz_mbar_wait(&acc_full, acc_phase);
+      if (dbg) w_accfull += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int er = (row < n) ? ea[row] : 0;
+      const double rs = __hiloint2double((1023 + er - 33) << 20, 0);  // 2^(e_i - 12 - 21)
+      const double* krow = sK + (quad * 32 + lane) * OZ_KLD;
       double qsum = 0.0;
-      for (int c0 = 0; c0 < OZ_BN; c0 += 8) {
+      for (int c0i = 0; c0i < OZ_BN; c0i += 8) {
         uint32_t g[OZ_NS][8];
 #pragma unroll
         for (int t = 0; t < OZ_NS; ++t)
-          oz_tmem_ld8(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * OZ_BN + c0), g[t]);
+          oz_tmem_ld8(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * OZ_BN + c0i), g[t]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < n) {
-          const int col = cb * OZ_BN + c0;
-          double out[8];
+        double out[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            double acc = (double)(int)g[OZ_NS - 1][j];
+        for (int j = 0; j < 8; ++j) {
+          // sum_t 2^(-7t) G_t = 2^-21 hi + 2^-49 lo with hi, lo exact 64-bit integers (< 2^47)
+          long long hi = (int)g[0][j], lo = (int)g[4][j];
 #pragma unroll
-            for (int t = OZ_NS - 2; t >= 0; --t) acc = fma(acc, 0.0078125, (double)(int)g[t][j]);
-            out[j] = ldexp(acc, er + eb[col + j] - 12);
+          for (int t = 1; t < 4; ++t) {
+            hi = hi * 128 + (int)g[t][j];
+            lo = lo * 128 + (int)g[4 + t][j];
           }
-          double* tp = T + (long)row * ldt + col;
+          const double val = fma((double)lo, 3.7252902984619140625e-9 /* 2^-28 */, (double)hi);
+          out[j] = val * rs * scol[c0i + j];
+        }
+        if (row < n) {
+          double* tp = T + (long)row * ldt + cb * OZ_BN + c0i;
 #pragma unroll
           for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(tp + j) = make_double2(out[j], out[j + 1]);
           if (q) {
-            const double* kp = Kmat + (long)row * ldk + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) qsum = fma(out[j], kp[j], qsum);
+            for (int j = 0; j < 8; j += 2) {
+              const double2 kk = *reinterpret_cast<const double2*>(krow + c0i + j);
+              qsum = fma(out[j], kk.x, qsum);
+              qsum = fma(out[j + 1], kk.y, qsum);
+            }
           }
         }
       }
@@ -243,18 +338,24 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       __syncwarp();
       if (lane == 0) oz_mbar_arrive(&acc_empty);
       acc_phase ^= 1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with sK / scol before the next tile overwrites them
     }
+    if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0) dbg[4] = w_accfull;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-constexpr int OZ_SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024;
+constexpr int OZ_SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + OZ_BM * OZ_KLD * 8 + 1024;
 
 }  // namespace npgp
 
 using namespace npgp;
+
+static long long* g_oz_dbg = nullptr;
+// debugging aid: device buffer of 8 counters filled by CTA 0 (cycles the producer / MMA issuer / epilogue spend waiting)
+extern "C" void npgp_rowquad_i8_debug(long long* dev_counters) { g_oz_dbg = dev_counters; }
 
 // workspace: A slices (ceil(n/128)*128 * Kd * 8 bytes) + C slices (N * Kd * 8) + exponents (int per padded row / column)
 extern "C" long npgp_rowquad_i8_workspace_bytes(int n, int M) {
@@ -276,9 +377,9 @@ extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const do
   int8_t* Bs = As + npad * M * OZ_NS;
   int* ea = reinterpret_cast<int*>(Bs + (long)M * M * OZ_NS);
   int* eb = ea + npad;
-  oz_slice_kernel<OZ_BM><<<(unsigned)((npad * 32 + 255) / 256), 256, 0, stream>>>(n, (int)npad, M, K, ldk, As, ea);
+  oz_slice_kernel<OZ_BM><<<(unsigned)(npad / 8), 512, 0, stream>>>(n, (int)npad, M, K, ldk, As, ea);
   NPGP_LAUNCH_CHECK();
-  oz_slice_kernel<OZ_BN><<<(unsigned)(((long)M * 32 + 255) / 256), 256, 0, stream>>>(M, M, M, C, ldc, Bs, eb);
+  oz_slice_kernel<OZ_BN><<<(unsigned)(M / 8), 512, 0, stream>>>(M, M, M, C, ldc, Bs, eb);
   NPGP_LAUNCH_CHECK();
   static bool attr_set = false;
   if (!attr_set) {
@@ -287,7 +388,7 @@ extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const do
   }
   const int tiles = (int)(npad / OZ_BM) * (M / OZ_BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  oz_rowquad_kernel<<<grid, OZ_THREADS, OZ_SMEM, stream>>>(n, M, M, As, ea, Bs, eb, K, ldk, T, ldt, q);
+  oz_rowquad_kernel<<<grid, OZ_THREADS, OZ_SMEM, stream>>>(n, M, M, As, ea, Bs, eb, K, ldk, T, ldt, q, g_oz_dbg);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

@@ -48,4 +48,10 @@ if __name__ == "__main__":
     case(300, 128, seed=1)
     case(1000, 256, seed=2)
     if len(sys.argv) > 1:
+        from nonstationary_precip_b200._lib import lib
+        dbg = torch.zeros(8, dtype=torch.int64, device="cuda")
+        lib().npgp_rowquad_i8_debug(dbg.data_ptr())
         case(65536, 1024, seed=3, bench=True)
+        names = ["producer_wait_empty", "mma_wait_acc_empty", "mma_wait_full", "mma_total", "epilogue_wait_acc_full"]
+        print(json.dumps(dict(zip(names, dbg.tolist()[:5]))))
+        lib().npgp_rowquad_i8_debug(None)
