@@ -202,6 +202,7 @@ def run_ours(args):
     kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_params(args.variant, M_IND, DIM).items()}
     Z = x_h[perm[:M_IND]].to(dev)
     model = SVGPGibbs(args.variant, Z, N_TOTAL, **kw)
+    model.rowquad_impl = args.gemm
     X, Y = x_h.to(dev), y_h.to(dev)  # whole data set resident in HBM (33 MB)
     Bl = B_GLOBAL // world
     nb = N_TOTAL // B_GLOBAL
@@ -358,6 +359,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="full", choices=["full", "diag"])
     ap.add_argument("--lr", type=float, default=0.01)
+    ap.add_argument("--gemm", default="dmma", choices=["dmma", "i8"],
+                    help="row-quadratic GEMM: FP64 DMMA (dgemm.cu) or exact int8 Ozaki split on tcgen05 (ozaki.cu)")
     ap.add_argument("--exec", default="graph", choices=["graph", "eager"],
                     help="replay the step as a captured CUDA graph (default) or launch it eagerly")
     ap.add_argument("--ref-rows", type=int, default=16384, help="minibatch rows the CPU reference processes per step")

@@ -116,6 +116,9 @@ class SVGPGibbs:
         self._side = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self._side2 = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self.overlap = True
+        # row-quadratic GEMM T = K C: "dmma" (FP64 tensor pipe, dgemm.cu) or "i8" (exact Ozaki split on tcgen05 int8,
+        # ozaki.cu; needs M % 64 == 0).  Same result to FP64 rounding (tests/test_ozaki_gpu.py).
+        self.rowquad_impl = "dmma"
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
 
@@ -175,6 +178,11 @@ class SVGPGibbs:
         if self.variant == "diag":
             return torch.exp(self.p["log_ell_z"])
         return self.o.sigma_from_h_fwd(self.p["H"], self.p["D"])
+
+    def _rowquad(self, K, C, T=None):
+        if self.rowquad_impl == "i8" and self.M % 64 == 0 and hasattr(self.o, "rowquad_i8"):
+            return self.o.rowquad_i8(K, C, T=T)
+        return self.o.rowquad(K, C, T=T)
 
     def _fork(self):
         """Run the enclosed launches on the side stream, ordered after everything enqueued so far."""
@@ -283,7 +291,7 @@ class SVGPGibbs:
         with self._sec("kxz_fwd"):
             K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
         with self._sec("rowquad"):
-            T, q = o.rowquad(K, C)
+            T, q = self._rowquad(K, C)
         acc, gmu, gv, _ = o.gauss_ell(yb, mu, q, s, noise, self.jitter_xx, 1e-6, 1.0 / Bg)
         ell = acc[0] / Bg
 
@@ -479,7 +487,7 @@ class SVGPGibbs:
                 K = torch.empty(xc.shape[0], self.M, dtype=torch.float64, device=self.dev)
                 T = torch.empty_like(K)
             _, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"], out=K)
-            _, q = o.rowquad(K, zz["C"], T=T)
+            _, q = self._rowquad(K, zz["C"], T=T)
             mean[lo:lo + chunk] = mu
             var[lo:lo + chunk] = (s + self.jitter_xx + q).clamp_min(1e-6)
         return mean, var
