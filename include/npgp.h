@@ -162,6 +162,12 @@ void npgp_rowquad_i8_debug(long long* dev_counters); /* optional: 8 cycle counte
 int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
                     void* work, long work_bytes, npgp_stream_t stream);
 
+/* alpha * w0 * K^T K (symmetric M x M, M % 128 == 0) on the integer tensor cores: the equal-weights case of npgp_wsyrk
+ * (w0 = *w0_dev, NULL: 1).  work: npgp_syrk_i8_workspace_bytes(n, M) bytes. */
+long npgp_syrk_i8_workspace_bytes(int n, int M);
+int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, double* Out, long ldo,
+                 void* work, long work_bytes, npgp_stream_t stream);
+
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 

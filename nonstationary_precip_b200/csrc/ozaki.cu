@@ -39,10 +39,43 @@ constexpr int OZ_THREADS = 192;
 //   byte offset = ((((r / BR) * nks + k / 32) * 8 + p) * 2 + (k % 32) / 16) * (BR * 16) + ((r % BR) / 8) * 128 + (r % 8) * 16 + k % 16
 // expo[r]: x = X[r, :] * 2^-expo[r] in [-1, 1]
 // ---------------------------------------------------------------------------------------------------------------------
-// CTA = 8 consecutive rows x 64 chunks of 16 columns (512 threads, Kd <= 1024 per pass; longer rows loop): thread
-// (row = t % 8, chunk = t / 8) keeps its 16 values in registers, the row maximum is reduced through shuffles + shared
-// memory, and every slice is written as ONE 16-byte vector; the 8 lanes of a row group write 128 contiguous bytes (one
-// core matrix).
+// Slices of 16 consecutive K-dimension entries v[j] * sc (|v sc| < 2^55): y = rint(v sc) is written in balanced base-128
+// digits, y = sum_p d_p 128^(7-p), d_p in [-64, 64], extracted as the unsigned digits of y + 64 (128^8 - 1)/127 (integer
+// shifts and masks only; the FP64 pipe sees one multiply and one conversion per entry).  Digit p of the 16 entries is one
+// 16-byte vector, stored at base + p * slice_stride.
+__device__ __forceinline__ void oz_store_slices(const double (&v)[16], double sc, int8_t* base, long slice_stride) {
+  constexpr unsigned long long BIAS = 64ull * ((1ull << 56) - 1ull) / 127ull;
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const unsigned long long u = (unsigned long long)(__double2ll_rn(v[j] * sc) + (long long)BIAS);
+    lo[j] = (uint32_t)(u & 0xFFFFFFFull);  // digits 4..7
+    hi[j] = (uint32_t)(u >> 28);           // digits 0..3 (the top one may reach 128)
+  }
+#pragma unroll
+  for (int p = 0; p < OZ_NS; ++p) {
+    uint32_t w[4];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b4 = 0; b4 < 4; ++b4) {
+        const int j = g4 * 4 + b4;
+        const uint32_t src = (p < 4) ? hi[j] : lo[j];
+        const int sh = 7 * (3 - (p & 3));
+        const uint32_t dgt = (p == 0) ? (src >> sh) : ((src >> sh) & 127u);
+        word |= ((dgt - 64u) & 0xffu) << (8 * b4);
+      }
+      w[g4] = word;
+    }
+    *reinterpret_cast<uint4*>(base + (long)p * slice_stride) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// Row-wise slicing (operand rows = rows of X, contraction along the columns).  CTA = 8 consecutive rows x 64 chunks of
+// 16 columns (512 threads; longer rows loop): thread (row = t % 8, chunk = t / 8) keeps its 16 values in registers, the
+// row maximum is reduced through shuffles + shared memory; the 8 lanes of a row group write 128 contiguous bytes (one
+// core matrix) per slice.
 template <int BR>
 __global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, const double* __restrict__ X, long ldx,
                                                        int8_t* __restrict__ out, int* __restrict__ expo) {
@@ -51,7 +84,6 @@ __global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, 
   const int t = threadIdx.x, rr = t & 7, ch = t >> 3, warp = t >> 5;
   const int r = blockIdx.x * 8 + rr;
   const int nks = Kd / OZ_KS, nch = Kd / 16;
-  // pass 1: row maximum (values of the first 64 chunks stay in registers)
   double v[16];
   double mx = 0.0;
   for (int c = ch; c < nch; c += 64) {
@@ -83,43 +115,64 @@ __global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, 
   }
   __syncthreads();
   if (r >= Rpad) return;
-  const int e = sexp[rr];
-  const double sc = __hiloint2double((1023 + 6 - e) << 20, 0);  // 2^(6 - e)
+  const double sc = __hiloint2double((1023 + 55 - sexp[rr]) << 20, 0);  // 2^(55 - e)
   const long blk = (long)(r / BR) * nks;
   const int rin = ((r % BR) / 8) * 128 + (r % 8) * 16;
   for (int c = ch; c < nch; c += 64) {
-    if (c != ch) {
-      if (r < R) {
-        const double2* src = reinterpret_cast<const double2*>(X + (long)r * ldx + c * 16);
+    if (c != ch && r < R) {
+      const double2* src = reinterpret_cast<const double2*>(X + (long)r * ldx + c * 16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const double2 d = src[j];
-          v[2 * j] = d.x;
-          v[2 * j + 1] = d.y;
-        }
+      for (int j = 0; j < 8; ++j) {
+        const double2 d = src[j];
+        v[2 * j] = d.x;
+        v[2 * j + 1] = d.y;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] *= sc;  // x 2^6, in (-64, 64); exact
-    int8_t* base = out + ((blk + c / 2) * OZ_NS * 2 + (c & 1)) * (long)(BR * 16) + rin;
-#pragma unroll
-    for (int p = 0; p < OZ_NS; ++p) {
-      uint32_t w[4];
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) {
-          const int j = g4 * 4 + b4;
-          const double a = rint(v[j]);
-          word |= ((uint32_t)(int)a & 0xffu) << (8 * b4);
-          v[j] = (v[j] - a) * 128.0;  // exact: removes the leading 7 bits of the remainder
-        }
-        w[g4] = word;
-      }
-      *reinterpret_cast<uint4*>(base + (long)p * 2 * (BR * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    oz_store_slices(v, sc, out + ((blk + c / 2) * OZ_NS * 2 + (c & 1)) * (long)(BR * 16) + rin, 2L * (BR * 16));
   }
+}
+
+// Column maxima of |X| (R x Kd) as int64 bit patterns (non-negative doubles order like integers); cmax zeroed by the caller.
+__global__ void __launch_bounds__(256) oz_colmax_kernel(int R, int Kd, const double* __restrict__ X, long ldx,
+                                                        int rows_per_cta, unsigned long long* __restrict__ cmax) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= Kd) return;
+  const int i0 = blockIdx.y * rows_per_cta, i1 = min(R, i0 + rows_per_cta);
+  double m = 0.0;
+  for (int i = i0; i < i1; ++i) m = fmax(m, fabs(X[(long)i * ldx + j]));
+  atomicMax(&cmax[j], (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void oz_exp_from_max_kernel(int n, const unsigned long long* __restrict__ cmax, int* __restrict__ expo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double m = __longlong_as_double((long long)cmax[j]);
+  int e = 0;
+  if (m > 0.0) frexp(m, &e);
+  expo[j] = e;
+}
+
+// Transposed slicing for the SYRK: operand rows = columns j of X (R x Kd), contraction along the rows i.  CTA = one
+// k-stage (32 rows i) x 128 columns j: coalesced reads along j, transpose through shared memory, thread (j, half) slices
+// the 16 consecutive i of its half stage.  Layout as oz_slice_kernel<128> with (row, k) = (j, i).
+__global__ void __launch_bounds__(256) oz_slice_t_kernel(int R, int Kd, const double* __restrict__ X, long ldx,
+                                                         const int* __restrict__ expo, int8_t* __restrict__ out) {
+  __shared__ double tile[32][129];
+  const int ks = blockIdx.x, jb = blockIdx.y, nks = gridDim.x;
+  for (int e = threadIdx.x; e < 32 * 128; e += 256) {
+    const int i = e >> 7, j = e & 127;
+    const int gi = ks * 32 + i, gj = jb * 128 + j;
+    tile[i][j] = (gi < R && gj < Kd) ? X[(long)gi * ldx + gj] : 0.0;
+  }
+  __syncthreads();
+  const int j = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int gj = jb * 128 + j;
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = tile[half * 16 + k][j];
+  const double sc = __hiloint2double((1023 + 55 - ((gj < Kd) ? expo[gj] : 0)) << 20, 0);
+  int8_t* base = out + (((long)jb * nks + ks) * OZ_NS * 2 + half) * (long)(OZ_BM * 16) + (j / 8) * 128 + (j % 8) * 16;
+  oz_store_slices(v, sc, base, 2L * (OZ_BM * 16));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -347,6 +400,160 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Out (M x M, upper 128 x 64 tiles) += alpha * w0 * X^T X from the transposed slices (operand rows = columns of X).  The
+// contraction runs over the R rows of X; it is cut into chunks of `stages_per_chunk` k-stages (<= 256 = 8192 rows, so that
+// |G_t| < 8 * 8192 * 2^12 = 2^28 stays exact in int32) and every (tile, chunk) work item adds its FP64 result atomically.
+// Both operands come from the same 128-row-block layout: the B operand (64 columns) is one half of a block, fetched as 16
+// pieces of 1 KB per stage.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restrict__ Xs, const int* __restrict__ ex,
+               double alpha, const double* __restrict__ w0, double* __restrict__ Out, long ldo) {
+  extern __shared__ __align__(1024) uint8_t oz_sm[];
+  uint8_t* sA = oz_sm;
+  uint8_t* sB = oz_sm + OZ_STAGES * OZ_A_STAGE;
+  __shared__ __align__(8) uint64_t full[OZ_STAGES], empty[OZ_STAGES], acc_full, acc_empty;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double scol[OZ_BN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_rb = M / OZ_BM, n_cb = M / OZ_BN;
+  const int n_tiles = n_rb * n_cb - n_rb * (n_rb - 1);  // sum_rb (n_cb - 2 rb): tiles with cb >= 2 rb
+  const int n_chunks = (nks_total + stages_per_chunk - 1) / stages_per_chunk;
+  const int n_items = n_tiles * n_chunks;
+  auto decode = [&](int item, int& rb, int& cb, int& k0, int& k1) {
+    int tl = item / n_chunks;
+    const int chunk = item % n_chunks;
+    rb = 0;
+    while (tl >= n_cb - 2 * rb) {
+      tl -= n_cb - 2 * rb;
+      ++rb;
+    }
+    cb = 2 * rb + tl;
+    k0 = chunk * stages_per_chunk;
+    k1 = min(nks_total, k0 + stages_per_chunk);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      oz_mbar_init(&full[s], 1);
+      oz_mbar_init(&empty[s], 1);
+    }
+    oz_mbar_init(&acc_full, 1);
+    oz_mbar_init(&acc_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int rb, cb, k0, k1;
+        decode(item, rb, cb, k0, k1);
+        const int8_t* a = Xs + (long)rb * nks_total * OZ_A_STAGE;
+        const int8_t* b = Xs + (long)(cb >> 1) * nks_total * OZ_A_STAGE + (cb & 1) * (OZ_BN * 16);
+        for (int ks = k0; ks < k1; ++ks) {
+          oz_mbar_wait(&empty[stage], phase ^ 1);
+          oz_mbar_expect_tx(&full[stage], OZ_A_STAGE + OZ_B_STAGE);
+          oz_bulk_g2s(sA + stage * OZ_A_STAGE, a + (long)ks * OZ_A_STAGE, OZ_A_STAGE, &full[stage]);
+#pragma unroll
+          for (int pp = 0; pp < 2 * OZ_NS; ++pp)  // (slice, plane) pieces: 64 rows x 16 bytes each
+            oz_bulk_g2s(sB + stage * OZ_B_STAGE + pp * (OZ_BN * 16), b + (long)ks * OZ_A_STAGE + pp * (OZ_BM * 16),
+                        OZ_BN * 16, &full[stage]);
+          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int rb, cb, k0, k1;
+        decode(item, rb, cb, k0, k1);
+        oz_mbar_wait(&acc_empty, acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ks = k0; ks < k1; ++ks) {
+          oz_mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = oz_smem(sA + stage * OZ_A_STAGE), b0 = oz_smem(sB + stage * OZ_B_STAGE);
+#pragma unroll
+          for (int p = 0; p < OZ_NS; ++p) {
+            const uint64_t da = oz_desc(a0 + p * (2 * OZ_BM * 16), OZ_BM * 16, 128);
+#pragma unroll
+            for (int qq = 0; qq < OZ_NS; ++qq) {
+              if (p + qq < OZ_NS) {
+                const uint64_t db = oz_desc(b0 + qq * (2 * OZ_BN * 16), OZ_BN * 16, 128);
+                oz_mma_i8(tmem + (uint32_t)((p + qq) * OZ_BN), da, db, idesc, (ks > k0 || p > 0) ? 1u : 0u);
+              }
+            }
+          }
+          oz_commit(&empty[stage]);
+          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+        }
+        oz_commit(&acc_full);
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3, et = tid - 64;
+    uint32_t acc_phase = 0;
+    const double aw = alpha * (w0 ? w0[0] : 1.0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int rb, cb, k0, k1;
+      decode(item, rb, cb, k0, k1);
+      const int row = rb * OZ_BM + quad * 32 + lane;
+      if (et < OZ_BN) scol[et] = __hiloint2double((1023 + ex[cb * OZ_BN + et]) << 20, 0);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      oz_mbar_wait(&acc_full, acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const double rs = aw * __hiloint2double((1023 + ex[row] - 33) << 20, 0);
+      for (int c0i = 0; c0i < OZ_BN; c0i += 8) {
+        uint32_t g[OZ_NS][8];
+#pragma unroll
+        for (int t = 0; t < OZ_NS; ++t)
+          oz_tmem_ld8(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * OZ_BN + c0i), g[t]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double* op = Out + (long)row * ldo + cb * OZ_BN + c0i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          long long hi = (int)g[0][j], lo = (int)g[4][j];
+#pragma unroll
+          for (int t = 1; t < 4; ++t) {
+            hi = hi * 128 + (int)g[t][j];
+            lo = lo * 128 + (int)g[4 + t][j];
+          }
+          const double val = fma((double)lo, 3.7252902984619140625e-9 /* 2^-28 */, (double)hi);
+          atomicAdd(op + j, val * rs * scol[c0i + j]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) oz_mbar_arrive(&acc_empty);
+      acc_phase ^= 1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+__global__ void oz_symmetrize_upper_kernel(int M, double* C, long ldc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (r < M && c < M && c < r) C[(long)r * ldc + c] = C[(long)c * ldc + r];
+}
+
 constexpr int OZ_SMEM = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + OZ_BM * OZ_KLD * 8 + 1024;
 
 }  // namespace npgp
@@ -389,6 +596,73 @@ extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const do
   const int tiles = (int)(npad / OZ_BM) * (M / OZ_BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   oz_rowquad_kernel<<<grid, OZ_THREADS, OZ_SMEM, stream>>>(n, M, M, As, ea, Bs, eb, K, ldk, T, ldt, q, g_oz_dbg);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// workspace: transposed slices (M * ceil(n/32)*32 * 8 bytes) + column maxima (8 bytes each) + exponents
+extern "C" long npgp_syrk_i8_workspace_bytes(int n, int M) {
+  const long npad = ((long)n + OZ_KS - 1) / OZ_KS * OZ_KS;
+  return npad * M * OZ_NS + (long)M * (sizeof(unsigned long long) + sizeof(int)) + 1024;
+}
+
+// Out (M x M, symmetric) = alpha * w0 * K^T K with w0 = *w0_dev (NULL: 1), K (n x M); M must be a multiple of 128.
+// The unweighted / equal-weights case of npgp_wsyrk on the integer tensor cores (exact Ozaki split).
+extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, double* Out,
+                            long ldo, void* work, long work_bytes, cudaStream_t stream) {
+  if (n < 0 || M < 0) return NPGP_EINVAL;
+  if (M == 0) return NPGP_OK;
+  if (!Out || (n > 0 && !K) || !work) return NPGP_EINVAL;
+  if (M % OZ_BM) return NPGP_EUNSUPPORTED;
+  if (work_bytes < npgp_syrk_i8_workspace_bytes(n, M)) return NPGP_EWORKSPACE;
+  const long npad = ((long)n + OZ_KS - 1) / OZ_KS * OZ_KS;
+  const int nks = (int)(npad / OZ_KS);
+  int8_t* Xs = static_cast<int8_t*>(work);
+  unsigned long long* cmax = reinterpret_cast<unsigned long long*>(Xs + npad * M * OZ_NS);
+  int* ex = reinterpret_cast<int*>(cmax + M);
+  NPGP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned long long) * M, stream));
+  NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
+  if (n == 0) return NPGP_OK;
+  {
+    const int rows_per_cta = 256;
+    dim3 grid(ceil_div(M, 256), ceil_div(n, rows_per_cta));
+    oz_colmax_kernel<<<grid, 256, 0, stream>>>(n, M, K, ldk, rows_per_cta, cmax);
+    NPGP_LAUNCH_CHECK();
+    oz_exp_from_max_kernel<<<ceil_div(M, 256), 256, 0, stream>>>(M, cmax, ex);
+    NPGP_LAUNCH_CHECK();
+    dim3 gs(nks, M / OZ_BM);
+    oz_slice_t_kernel<<<gs, 256, 0, stream>>>(n, M, K, ldk, ex, Xs);
+    NPGP_LAUNCH_CHECK();
+  }
+  static bool attr_set = false;
+  constexpr int smem = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024;
+  if (!attr_set) {
+    NPGP_CUDA(cudaFuncSetAttribute(oz_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int n_rb = M / OZ_BM, n_cb = M / OZ_BN;
+  const int n_tiles = n_rb * n_cb - n_rb * (n_rb - 1);
+  // chunks of at most 256 stages (int32 exactness); among the admissible chunk counts take the one whose work items fill
+  // whole rounds of the persistent CTAs best (cost = rounds x stages per chunk)
+  const int min_chunks = ceil_div(nks, 256);
+  int best_chunks = min_chunks;
+  long best_cost = -1;
+  for (int c = min_chunks; c <= min_chunks + 64 && c <= nks; ++c) {
+    const int spc_c = ceil_div(nks, c);
+    if (spc_c < 16 && c > min_chunks) break;
+    const long rounds = ((long)n_tiles * ceil_div(nks, spc_c) + kNumSMs - 1) / kNumSMs;
+    const long cost = rounds * (spc_c + 4);  // + epilogue, in units of a k-stage
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_chunks = c;
+    }
+  }
+  const int spc = ceil_div(nks, best_chunks);
+  const int items = n_tiles * ceil_div(nks, spc);
+  oz_syrk_kernel<<<items < kNumSMs ? items : kNumSMs, OZ_THREADS, smem, stream>>>(M, nks, spc, Xs, ex, alpha, w0_dev, Out, ldo);
+  NPGP_LAUNCH_CHECK();
+  dim3 blk(32, 8), grd(ceil_div(M, 32), ceil_div(M, 8));
+  oz_symmetrize_upper_kernel<<<grd, blk, 0, stream>>>(M, Out, ldo);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

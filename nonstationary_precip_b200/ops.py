@@ -184,6 +184,22 @@ def rowquad_i8(K, Cm, need_q=True, T=None):
     return T, q
 
 
+def syrk_i8(K, w0=None, alpha=1.0, out=None):
+    """alpha * w0 * K^T K (symmetric M x M) on the integer tensor cores (exact Ozaki split, csrc/ozaki.cu); w0: device
+    scalar (or None); M must be a multiple of 128."""
+    n, M = K.shape
+    if out is None:
+        out = torch.empty(M, M, dtype=torch.float64, device=K.device)
+    nbytes = lib().npgp_syrk_i8_workspace_bytes(n, M)
+    key = ("syrk", K.device.index, n, M)
+    work = _I8_WORK.get(key)
+    if work is None:
+        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
+    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), ptr(out), out.stride(0), ptr(work), nbytes,
+                             stream()), "npgp_syrk_i8")
+    return out
+
+
 def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0):
     """alpha * K^T diag(w) K (symmetric M x M).  uniform_count (device scalar) == uniform_target tells the kernel, on
     the device, that all weights are equal."""
