@@ -163,10 +163,16 @@ int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, lo
                     void* work, long work_bytes, npgp_stream_t stream);
 
 /* alpha * w0 * K^T K (symmetric M x M, M % 128 == 0) on the integer tensor cores: the equal-weights case of npgp_wsyrk
- * (w0 = *w0_dev, NULL: 1).  work: npgp_syrk_i8_workspace_bytes(n, M) bytes. */
+ * (w0 = *w0_dev, NULL: 1).  uniform_count / uniform_target (optional): device-side gate as in npgp_wsyrk_hint, the kernel
+ * only runs when *uniform_count == uniform_target; accumulate != 0 adds to Out.  work: npgp_syrk_i8_workspace_bytes(n, M).
+ * npgp_wsyrk_weighted_only is the complementary half: Out = alpha K^T diag(w) K when the weights are NOT all equal, else 0. */
 long npgp_syrk_i8_workspace_bytes(int n, int M);
-int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, double* Out, long ldo,
-                 void* work, long work_bytes, npgp_stream_t stream);
+int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, const double* uniform_count,
+                 double uniform_target, int accumulate, double* Out, long ldo, void* work, long work_bytes,
+                 npgp_stream_t stream);
+int npgp_wsyrk_weighted_only(int n, int M, double alpha, const double* K, long ldk, const double* w,
+                             const double* uniform_count, double uniform_target, double* Out, long ldo,
+                             npgp_stream_t stream);
 
 /* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);

@@ -51,6 +51,7 @@ struct GemmParams {
   const double* w;   // optional weights along K (scales op(A)[m][k] by w[k])
   const double* w_uniform_count;  // optional device scalar: if *w_uniform_count == w_uniform_target every weight equals
   double w_uniform_target;        //   w[0], so the kernel skips the per-fragment multiplies and scales the epilogue
+  int weighted_only;              // launch only the weighted instantiation (the equal-weights case is handled elsewhere)
   const double* dotK;  // optional: q[row] += sum_col acc[row][col] * dotK[row][col]
   long lddot;
   double* q;
@@ -322,8 +323,10 @@ static int launch_cfg(const GemmParams& p, cudaStream_t st) {
   }
   dim3 grid(ceil_div(p.N, Cfg::BN), ceil_div(p.M, Cfg::BM), p.splits);
   if (p.w && p.w_uniform_count) {
-    kern<<<grid, GEMM_THREADS, smem, st>>>(p);
-    NPGP_LAUNCH_CHECK();
+    if (!p.weighted_only) {
+      kern<<<grid, GEMM_THREADS, smem, st>>>(p);
+      NPGP_LAUNCH_CHECK();
+    }
     kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
   } else if (p.w) {
     kern_w<<<grid, GEMM_THREADS, smem, st>>>(p);
@@ -419,7 +422,8 @@ extern "C" int npgp_rowquad(int n, int M, const double* K, long ldk, const doubl
 
 // Out (M x M, symmetric) = alpha * K^T diag(w) K, K is (n x M); w may be NULL.  Out is overwritten.
 static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, const double* w,
-                      const double* w_uniform_count, double w_uniform_target, double* Out, long ldo, cudaStream_t stream);
+                      const double* w_uniform_count, double w_uniform_target, double* Out, long ldo, cudaStream_t stream,
+                      int weighted_only = 0);
 
 extern "C" int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const double* w, double* Out, long ldo,
                           cudaStream_t stream) {
@@ -437,7 +441,7 @@ extern "C" int npgp_wsyrk_hint(int n, int M, double alpha, const double* K, long
 
 static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, const double* w,
                       const double* w_uniform_count, double w_uniform_target, double* Out, long ldo,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int weighted_only) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
   if (!Out || (n > 0 && !K)) return NPGP_EINVAL;
@@ -446,6 +450,7 @@ static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, con
   p.M = M; p.N = M; p.K = n; p.A = K; p.lda = ldk; p.B = K; p.ldb = ldk; p.C = Out; p.ldc = ldo;
   p.alpha = alpha; p.beta = 0.0; p.out_tri = 2; p.w = w;
   p.w_uniform_count = w ? w_uniform_count : nullptr; p.w_uniform_target = w_uniform_target;
+  p.weighted_only = weighted_only;
   const long tiles = ((long)ceil_div(M, tile_bm()) * ceil_div(M, tile_bn()) + ceil_div(M, tile_bm())) / 2;
   // split the row range so that tiles x splits fills whole waves of resident CTAs: the cost of a choice is
   // (number of waves) / splits; take the cheapest among 1..32 splits of at least 512 rows each
@@ -461,10 +466,11 @@ static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, con
     }
   }
   p.splits = best_s;
-  if (p.splits > 1) {
+  if (p.splits > 1 || weighted_only) {  // weighted_only: the kernel may exit without writing
     const long tot = (long)M * M;
     scale_matrix_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(M, M, Out, ldo, 0.0, 0);
     NPGP_LAUNCH_CHECK();
+    if (weighted_only && p.splits == 1) p.beta = 1.0;
   }
   int rc = launch_gemm(false, false, p, stream);
   if (rc) return rc;
@@ -472,6 +478,15 @@ static int wsyrk_impl(int n, int M, double alpha, const double* K, long ldk, con
   symmetrize_kernel<<<grd, blk, 0, stream>>>(M, Out, ldo, 1);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
+}
+
+// The unequal-weights half of npgp_wsyrk_hint: Out = alpha K^T diag(w) K if *uniform_count != uniform_target, else Out = 0
+// (the equal-weights case is then added by npgp_syrk_i8 with accumulate = 1).
+extern "C" int npgp_wsyrk_weighted_only(int n, int M, double alpha, const double* K, long ldk, const double* w,
+                                        const double* uniform_count, double uniform_target, double* Out, long ldo,
+                                        cudaStream_t stream) {
+  if (!w || !uniform_count) return NPGP_EINVAL;
+  return wsyrk_impl(n, M, alpha, K, ldk, w, uniform_count, uniform_target, Out, ldo, stream, 1);
 }
 
 extern "C" int npgp_symmetrize(int M, double* C, long ldc, int from_upper, cudaStream_t stream) {

@@ -409,7 +409,9 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restrict__ Xs, const int* __restrict__ ex,
-               double alpha, const double* __restrict__ w0, double* __restrict__ Out, long ldo) {
+               double alpha, const double* __restrict__ w0, const double* __restrict__ uniform_count,
+               double uniform_target, double* __restrict__ Out, long ldo) {
+  if (uniform_count && *uniform_count != uniform_target) return;  // unequal weights: the FP64 weighted kernel handles it
   extern __shared__ __align__(1024) uint8_t oz_sm[];
   uint8_t* sA = oz_sm;
   uint8_t* sB = oz_sm + OZ_STAGES * OZ_A_STAGE;
@@ -608,8 +610,11 @@ extern "C" long npgp_syrk_i8_workspace_bytes(int n, int M) {
 
 // Out (M x M, symmetric) = alpha * w0 * K^T K with w0 = *w0_dev (NULL: 1), K (n x M); M must be a multiple of 128.
 // The unweighted / equal-weights case of npgp_wsyrk on the integer tensor cores (exact Ozaki split).
-extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, double* Out,
-                            long ldo, void* work, long work_bytes, cudaStream_t stream) {
+// uniform_count / uniform_target (optional): the kernel only runs when *uniform_count == uniform_target (device-side
+// gate, see npgp_wsyrk_hint); accumulate != 0: add to Out instead of overwriting it.
+extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev,
+                            const double* uniform_count, double uniform_target, int accumulate, double* Out, long ldo,
+                            void* work, long work_bytes, cudaStream_t stream) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
   if (!Out || (n > 0 && !K) || !work) return NPGP_EINVAL;
@@ -621,7 +626,7 @@ extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ld
   unsigned long long* cmax = reinterpret_cast<unsigned long long*>(Xs + npad * M * OZ_NS);
   int* ex = reinterpret_cast<int*>(cmax + M);
   NPGP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned long long) * M, stream));
-  NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
+  if (!accumulate) NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
   if (n == 0) return NPGP_OK;
   {
     const int rows_per_cta = 256;
@@ -659,7 +664,8 @@ extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ld
   }
   const int spc = ceil_div(nks, best_chunks);
   const int items = n_tiles * ceil_div(nks, spc);
-  oz_syrk_kernel<<<items < kNumSMs ? items : kNumSMs, OZ_THREADS, smem, stream>>>(M, nks, spc, Xs, ex, alpha, w0_dev, Out, ldo);
+  oz_syrk_kernel<<<items < kNumSMs ? items : kNumSMs, OZ_THREADS, smem, stream>>>(M, nks, spc, Xs, ex, alpha, w0_dev, uniform_count,
+                                                                                       uniform_target, Out, ldo);
   NPGP_LAUNCH_CHECK();
   dim3 blk(32, 8), grd(ceil_div(M, 32), ceil_div(M, 8));
   oz_symmetrize_upper_kernel<<<grd, blk, 0, stream>>>(M, Out, ldo);

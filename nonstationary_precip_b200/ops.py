@@ -184,19 +184,42 @@ def rowquad_i8(K, Cm, need_q=True, T=None):
     return T, q
 
 
+def _syrk_i8_work(K):
+    n, M = K.shape
+    nbytes = lib().npgp_syrk_i8_workspace_bytes(n, M)
+    key = ("syrk", K.device.index, n, M)
+    work = _I8_WORK.get(key)
+    if work is None:
+        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
+    return work, nbytes
+
+
 def syrk_i8(K, w0=None, alpha=1.0, out=None):
     """alpha * w0 * K^T K (symmetric M x M) on the integer tensor cores (exact Ozaki split, csrc/ozaki.cu); w0: device
     scalar (or None); M must be a multiple of 128."""
     n, M = K.shape
     if out is None:
         out = torch.empty(M, M, dtype=torch.float64, device=K.device)
-    nbytes = lib().npgp_syrk_i8_workspace_bytes(n, M)
-    key = ("syrk", K.device.index, n, M)
-    work = _I8_WORK.get(key)
-    if work is None:
-        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
-    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), ptr(out), out.stride(0), ptr(work), nbytes,
-                             stream()), "npgp_syrk_i8")
+    work, nbytes = _syrk_i8_work(K)
+    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), None, 0.0, 0, ptr(out), out.stride(0),
+                             ptr(work), nbytes, stream()), "npgp_syrk_i8")
+    return out
+
+
+def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None):
+    """alpha * K^T diag(w) K with the device-side equal-weights gate of `wsyrk`: equal weights (the normal case of the
+    SVGP step) run on the integer tensor cores, unequal ones on the FP64 weighted kernel; both are enqueued and the one
+    the flag does not select exits at once."""
+    n, M = K.shape
+    if out is None:
+        out = torch.empty(M, M, dtype=torch.float64, device=K.device)
+    w = _c(w)
+    check(lib().npgp_wsyrk_weighted_only(n, M, float(alpha), ptr(K), K.stride(0), ptr(w), ptr(uniform_count),
+                                         float(uniform_target), ptr(out), out.stride(0), stream()),
+          "npgp_wsyrk_weighted_only")
+    work, nbytes = _syrk_i8_work(K)
+    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w), ptr(uniform_count), float(uniform_target), 1,
+                             ptr(out), out.stride(0), ptr(work), nbytes, stream()), "npgp_syrk_i8")
     return out
 
 

@@ -318,7 +318,10 @@ class SVGPGibbs:
                 du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
                 # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
-                dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
+                if self.rowquad_impl == "i8" and M % 128 == 0 and hasattr(o, "wsyrk_i8"):
+                    dC = o.wsyrk_i8(K, gv, acc[2:3], float(Bl))
+                else:
+                    dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
             if wsyrk_done is not None:
                 wsyrk_done.record()
             with self._sec("m3_bwd+kzz_bwd"):

@@ -69,6 +69,49 @@ def test_rowquad_i8_rejects_unsupported_shapes():
         ops.rowquad_i8(K, C)
 
 
+@pytest.mark.parametrize("n,M", [(1, 128), (33, 128), (1000, 128), (5000, 256), (20000, 1024)])
+def test_syrk_i8_matches_fp64(n, M):
+    from nonstationary_precip_b200 import ops
+    g = torch.Generator().manual_seed(n + M)
+    K = (torch.rand(n, M, generator=g) * torch.exp(2 * torch.randn(1, M, generator=g))).cuda()
+    w0 = torch.tensor([-0.37], device="cuda")
+    got = ops.syrk_i8(K, w0=w0, alpha=2.0)
+    want = -0.74 * (K.T @ K)
+    scale = 0.74 * (K.abs().T @ K.abs())
+    assert ((got - want).abs() / scale).max().item() < 1e-14
+    assert torch.equal(got, got.T)
+    ref = ops.wsyrk(K, alpha=-0.74)
+    assert ((got - ref).abs() / scale).max().item() < 1e-14
+
+
+def test_syrk_i8_exact_on_integer_data():
+    from nonstationary_precip_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    Ki = torch.randint(-2000, 2000, (3000, 128), generator=g)
+    got = ops.syrk_i8(Ki.double().cuda() * 2.0 ** -9)
+    assert torch.equal(got.cpu(), (Ki.T @ Ki).double() * 2.0 ** -18)
+
+
+def test_wsyrk_i8_device_gate():
+    """Equal weights -> integer tensor-core path; one differing weight -> the FP64 weighted kernel; both enqueued."""
+    from nonstationary_precip_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    n, M = 3000, 256
+    K = torch.rand(n, M, generator=g).cuda()
+    w = torch.full((n,), -0.25, device="cuda")
+    cnt = torch.tensor([float(n)], device="cuda")
+    got = ops.wsyrk_i8(K, w, cnt, float(n))
+    want = -0.25 * (K.T @ K)
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-13
+    w2 = w.clone()
+    w2[17] = 0.0
+    cnt2 = torch.tensor([float(n - 1)], device="cuda")
+    got2 = ops.wsyrk_i8(K, w2, cnt2, float(n))
+    want2 = K.T @ (w2[:, None] * K)
+    assert ((got2 - want2).abs().max() / want2.abs().max()).item() < 1e-13
+    assert torch.equal(got2, got2.T)
+
+
 @pytest.mark.parametrize("variant", ["full", "diag"])
 def test_svgp_step_with_i8_rowquad_matches_dmma_and_oracle(variant):
     """Whole ELBO step (loss + flat gradient) and prediction with rowquad_impl='i8': against the DMMA step on the same
