@@ -310,6 +310,34 @@ def run_ours(args):
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
     rq_tf = 2.0 * Bl * M_IND * M_IND / sec["rowquad"] / 1e9
+    i8_roof = None
+    if args.gemm == "i8":
+        # dominant kernel of the int8 path: oz_rowquad_kernel alone (slices from the last step are still in the workspace)
+        from nonstationary_precip_b200 import ops as _ops
+        Kt = torch.rand(Bl, M_IND, dtype=torch.float64, device=dev)
+        Ct = torch.eye(M_IND, dtype=torch.float64, device=dev)
+        Tt, _ = _ops.rowquad_i8(Kt, Ct)
+        work = _ops._I8_WORK[(dev.index, Bl, M_IND)]
+        nbytes = lib().npgp_rowquad_i8_workspace_bytes(Bl, M_IND)
+        best = float("inf")
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(lib().npgp_rowquad_i8_gemm_only(Bl, M_IND, ptr(Kt), Kt.stride(0), ptr(Tt), Tt.stride(0), None, ptr(work),
+                                                  nbytes, stream()), "gemm_only")
+            b.record()
+            b.synchronize()
+            best = min(best, a.elapsed_time(b))
+        top = 36 * 2.0 * Bl * M_IND * M_IND / best / 1e9  # 36 int8 slice products per FP64-exact product
+        i8_peak = 2.0 * peaks.get("bf16_tflops", 2250.0)
+        i8_roof = {"bound": "tensor", "kernel": "oz_rowquad_kernel (T = K C as 36 exact int8 slice products, tcgen05 kind::i8 "
+                                                "+ TMEM)", "achieved": top, "peak": i8_peak, "unit": "TFLOP/s",
+                   "frac": top / i8_peak, "ms": best, "fp64_equivalent_tflops": 2.0 * Bl * M_IND * M_IND / best / 1e9,
+                   # dram__bytes_read.sum + dram__bytes_write.sum at Bl = 65536 (ncu, profiles/r01_ncu_oz_kernels.txt):
+                   # slices 537 MB + K tile 537 MB read, T 507 MB written
+                   "traffic": 1.591e9 if world == 1 else None,
+                   "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x dense bf16 on B200; no measured "
+                                  "int8 entry); unit is int8 TOP/s"}
     kxz_gbs = 16.0 * Bl * M_IND / (sec["kxz_fwd"] + sec["kxz_bwd"]) / 1e6
 
     if rank == 0:
@@ -320,12 +348,17 @@ def run_ours(args):
         line = {
             "metric": "SVGP-Gibbs ELBO steps/s", "value": args.steps / (ms / 1e3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args), exec="cuda_graph + 2 streams" if args.exec == "graph" else "eager"),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.gemm == "dmma" else "f64 (the two large GEMMs as exact int8 slice products, int32 accumulation)",
+            "data": "synthetic",
+            "config": dict(workload_config(args), exec="cuda_graph + 3 streams" if args.exec == "graph" else "eager",
+                           gemm="FP64 DMMA" if args.gemm == "dmma" else
+                           "exact int8 Ozaki split on tcgen05 (FP64-equivalent results)"),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},
-            "roofline": {"bound": "tensor", "kernel": "dgemm_kernel (rowquad T = K C, FP64 DMMA)", "achieved": rq_tf,
+            "roofline": i8_roof if i8_roof is not None else {
+                         "bound": "tensor", "kernel": "dgemm_kernel (rowquad T = K C, FP64 DMMA)", "achieved": rq_tf,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": rq_tf / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at Bl = 65536 from the ncu --set full
                          # capture in profiles/r01_ncu_rowquad_full_summary.txt (algorithmic: 1082 MB)
@@ -359,7 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="full", choices=["full", "diag"])
     ap.add_argument("--lr", type=float, default=0.01)
-    ap.add_argument("--gemm", default="dmma", choices=["dmma", "i8"],
+    ap.add_argument("--gemm", default="i8", choices=["dmma", "i8"],
                     help="row-quadratic GEMM: FP64 DMMA (dgemm.cu) or exact int8 Ozaki split on tcgen05 (ozaki.cu)")
     ap.add_argument("--exec", default="graph", choices=["graph", "eager"],
                     help="replay the step as a captured CUDA graph (default) or launch it eagerly")

@@ -158,6 +158,8 @@ int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const do
  * Replaces the same reference lines as npgp_rowquad (k_ux1.matmul(...), models/gibbs_kernels.py:222-232; A^T (S - I) A of
  * the whitened SVGP). */
 long npgp_rowquad_i8_workspace_bytes(int n, int M);
+int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk, double* T, long ldt, double* q, void* work,
+                              long work_bytes, npgp_stream_t stream); /* measurement helper: GEMM on the slices left in work */
 void npgp_rowquad_i8_debug(long long* dev_counters); /* optional: 8 cycle counters written by CTA 0 (NULL = off) */
 int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
                     void* work, long work_bytes, npgp_stream_t stream);

@@ -574,8 +574,23 @@ extern "C" long npgp_rowquad_i8_workspace_bytes(int n, int M) {
 
 // T (n x M) = K (n x M) @ C (M x M, symmetric);  q[i] += sum_j T_ij K_ij (q zeroed by the caller; NULL to skip).
 // M must be a multiple of 64.  Replaces npgp_rowquad on the integer tensor-core path.
+static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
+                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice);
+
 extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
                                double* q, void* work, long work_bytes, cudaStream_t stream) {
+  return rowquad_i8_impl(n, M, K, ldk, C, ldc, T, ldt, q, work, work_bytes, stream, true);
+}
+
+// The tensor-core kernel alone, on the slices a previous npgp_rowquad_i8 call with the same shapes left in `work`
+// (measurement helper: times the GEMM without the slicing passes).
+extern "C" int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk, double* T, long ldt, double* q,
+                                         void* work, long work_bytes, cudaStream_t stream) {
+  return rowquad_i8_impl(n, M, K, ldk, K, 0, T, ldt, q, work, work_bytes, stream, false);
+}
+
+static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
+                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (n == 0 || M == 0) return NPGP_OK;
   if (!K || !C || !T || !work) return NPGP_EINVAL;
@@ -586,10 +601,12 @@ extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const do
   int8_t* Bs = As + npad * M * OZ_NS;
   int* ea = reinterpret_cast<int*>(Bs + (long)M * M * OZ_NS);
   int* eb = ea + npad;
-  oz_slice_kernel<OZ_BM><<<(unsigned)(npad / 8), 512, 0, stream>>>(n, (int)npad, M, K, ldk, As, ea);
-  NPGP_LAUNCH_CHECK();
-  oz_slice_kernel<OZ_BN><<<(unsigned)(M / 8), 512, 0, stream>>>(M, M, M, C, ldc, Bs, eb);
-  NPGP_LAUNCH_CHECK();
+  if (slice) {
+    oz_slice_kernel<OZ_BM><<<(unsigned)(npad / 8), 512, 0, stream>>>(n, (int)npad, M, K, ldk, As, ea);
+    NPGP_LAUNCH_CHECK();
+    oz_slice_kernel<OZ_BN><<<(unsigned)(M / 8), 512, 0, stream>>>(M, M, M, C, ldc, Bs, eb);
+    NPGP_LAUNCH_CHECK();
+  }
   static bool attr_set = false;
   if (!attr_set) {
     NPGP_CUDA(cudaFuncSetAttribute(oz_rowquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
