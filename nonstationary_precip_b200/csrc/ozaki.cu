@@ -219,6 +219,20 @@ __device__ __forceinline__ void oz_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void oz_commit(uint64_t* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem(b)) : "memory");
 }
+// one elected lane of a fully active warp (the form the compiler recognises: a tcgen05 instruction under this predicate is
+// issued once, without the elect-and-retry loop it wraps around the same instruction in a `lane == 0` branch)
+__device__ __forceinline__ bool oz_elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+// shared-memory descriptors of one stage differ only in the 14-bit start-address field of the low word
+__device__ __forceinline__ uint64_t oz_desc_hi_lo(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -285,10 +299,12 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       if (dbg && blockIdx.x == 0) dbg[0] = w_empty;
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow), one elected lane issues =====
+    {
+      const bool leader = oz_elect_one();
       // c_format S32 (2) @4, a/b format INT8 (1) @7/@10, both K-major, N>>3 @17, M>>4 @24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      constexpr uint32_t kHiDesc = (128u >> 4) | (1u << 14);  // stride byte offset 128, descriptor version 1
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       long long w_acc = 0, w_full = 0, t_all = dbg ? clock64() : 0;
@@ -302,25 +318,31 @@ oz_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
           oz_mbar_wait(&full[stage], phase);
           if (dbg) w_full += clock64() - c0;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = oz_smem(sA + stage * OZ_A_STAGE), b0 = oz_smem(sB + stage * OZ_B_STAGE);
+          if (leader) {
+            const uint32_t a_lo = ((oz_smem(sA + stage * OZ_A_STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(OZ_BM * 16 >> 4) << 16);
+            const uint32_t b_lo = ((oz_smem(sB + stage * OZ_B_STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(OZ_BN * 16 >> 4) << 16);
+            const uint32_t first = ks > 0 ? 1u : 0u;
 #pragma unroll
-          for (int p = 0; p < OZ_NS; ++p) {
-            const uint64_t da = oz_desc(a0 + p * (2 * OZ_BM * 16), OZ_BM * 16, 128);
+            for (int p = 0; p < OZ_NS; ++p) {
+              const uint64_t da = oz_desc_hi_lo(a_lo + p * (2 * OZ_BM * 16 >> 4), kHiDesc);
 #pragma unroll
-            for (int qq = 0; qq < OZ_NS; ++qq) {
-              if (p + qq < OZ_NS) {
-                const uint64_t db = oz_desc(b0 + qq * (2 * OZ_BN * 16), OZ_BN * 16, 128);
-                oz_mma_i8(tmem + (uint32_t)((p + qq) * OZ_BN), da, db, idesc, (ks > 0 || p > 0) ? 1u : 0u);
+              for (int qq = 0; qq < OZ_NS; ++qq) {
+                if (p + qq < OZ_NS) {
+                  const uint64_t db = oz_desc_hi_lo(b_lo + qq * (2 * OZ_BN * 16 >> 4), kHiDesc);
+                  oz_mma_i8(tmem + (uint32_t)((p + qq) * OZ_BN), da, db, idesc, p > 0 ? 1u : first);
+                }
               }
             }
+            oz_commit(&empty[stage]);  // frees the stage when these MMAs have read it
           }
-          oz_commit(&empty[stage]);  // frees the stage when these MMAs have read it
+          __syncwarp();
           if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
         }
-        oz_commit(&acc_full);
+        if (leader) oz_commit(&acc_full);
+        __syncwarp();
         acc_phase ^= 1;
       }
-      if (dbg && blockIdx.x == 0) {
+      if (dbg && blockIdx.x == 0 && leader) {
         dbg[1] = w_acc;
         dbg[2] = w_full;
         dbg[3] = clock64() - t_all;
@@ -476,8 +498,10 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = oz_elect_one();
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      constexpr uint32_t kHiDesc = (128u >> 4) | (1u << 14);
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -488,22 +512,28 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
         for (int ks = k0; ks < k1; ++ks) {
           oz_mbar_wait(&full[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = oz_smem(sA + stage * OZ_A_STAGE), b0 = oz_smem(sB + stage * OZ_B_STAGE);
+          if (leader) {
+            const uint32_t a_lo = ((oz_smem(sA + stage * OZ_A_STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(OZ_BM * 16 >> 4) << 16);
+            const uint32_t b_lo = ((oz_smem(sB + stage * OZ_B_STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(OZ_BN * 16 >> 4) << 16);
+            const uint32_t first = ks > k0 ? 1u : 0u;
 #pragma unroll
-          for (int p = 0; p < OZ_NS; ++p) {
-            const uint64_t da = oz_desc(a0 + p * (2 * OZ_BM * 16), OZ_BM * 16, 128);
+            for (int p = 0; p < OZ_NS; ++p) {
+              const uint64_t da = oz_desc_hi_lo(a_lo + p * (2 * OZ_BM * 16 >> 4), kHiDesc);
 #pragma unroll
-            for (int qq = 0; qq < OZ_NS; ++qq) {
-              if (p + qq < OZ_NS) {
-                const uint64_t db = oz_desc(b0 + qq * (2 * OZ_BN * 16), OZ_BN * 16, 128);
-                oz_mma_i8(tmem + (uint32_t)((p + qq) * OZ_BN), da, db, idesc, (ks > k0 || p > 0) ? 1u : 0u);
+              for (int qq = 0; qq < OZ_NS; ++qq) {
+                if (p + qq < OZ_NS) {
+                  const uint64_t db = oz_desc_hi_lo(b_lo + qq * (2 * OZ_BN * 16 >> 4), kHiDesc);
+                  oz_mma_i8(tmem + (uint32_t)((p + qq) * OZ_BN), da, db, idesc, p > 0 ? 1u : first);
+                }
               }
             }
+            oz_commit(&empty[stage]);
           }
-          oz_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
         }
-        oz_commit(&acc_full);
+        if (leader) oz_commit(&acc_full);
+        __syncwarp();
         acc_phase ^= 1;
       }
     }
