@@ -118,7 +118,7 @@ class SVGPGibbs:
         self.overlap = True
         # row-quadratic GEMM T = K C: "dmma" (FP64 tensor pipe, dgemm.cu) or "i8" (exact Ozaki split on tcgen05 int8,
         # ozaki.cu; needs M % 64 == 0).  Same result to FP64 rounding (tests/test_ozaki_gpu.py).
-        self.rowquad_impl = "dmma"
+        self.rowquad_impl = "i8"  # falls back to "dmma" per call when M is not a multiple of 64 (SYRK: 128)
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
 
