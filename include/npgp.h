@@ -160,6 +160,8 @@ int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const do
 long npgp_rowquad_i8_workspace_bytes(int n, int M);
 int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk, double* T, long ldt, double* q, void* work,
                               long work_bytes, npgp_stream_t stream); /* measurement helper: GEMM on the slices left in work */
+int npgp_rowquad_i8_slice_only(int n, int M, const double* K, long ldk, const double* C, long ldc, void* work,
+                               long work_bytes, npgp_stream_t stream); /* slicing passes only; then ..._gemm_only */
 void npgp_rowquad_i8_debug(long long* dev_counters); /* optional: 8 cycle counters written by CTA 0 (NULL = off) */
 int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
                     void* work, long work_bytes, npgp_stream_t stream);
@@ -170,8 +172,8 @@ int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, lo
  * npgp_wsyrk_weighted_only is the complementary half: Out = alpha K^T diag(w) K when the weights are NOT all equal, else 0. */
 long npgp_syrk_i8_workspace_bytes(int n, int M);
 int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, const double* uniform_count,
-                 double uniform_target, int accumulate, double* Out, long ldo, void* work, long work_bytes,
-                 npgp_stream_t stream);
+                 double uniform_target, int accumulate, int phase, double* Out, long ldo, void* work, long work_bytes,
+                 npgp_stream_t stream); /* phase: 0 slice + run, 1 slicing passes only, 2 run on the slices left in work */
 int npgp_wsyrk_weighted_only(int n, int M, double alpha, const double* K, long ldk, const double* w,
                              const double* uniform_count, double uniform_target, double* Out, long ldo,
                              npgp_stream_t stream);

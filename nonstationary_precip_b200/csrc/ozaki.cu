@@ -27,7 +27,8 @@ constexpr int OZ_NS = 8;          // slices per operand
 constexpr int OZ_BM = 128;        // rows of K per tile (TMEM lanes)
 constexpr int OZ_BN = 64;         // columns per tile (TMEM columns per accumulator)
 constexpr int OZ_KS = 32;         // bytes of K per pipeline stage = one MMA k-step
-constexpr int OZ_STAGES = 3;
+constexpr int OZ_STAGES = 2;         // row-quadratic kernel (leaves shared memory for a co-resident slicer CTA; 3 measured equal)
+constexpr int OZ_SYRK_STAGES = 4;    // SYRK kernel (no K tile to stage)
 constexpr int OZ_KLD = OZ_BN + 2;     // leading dimension (doubles) of the staged K tile: conflict-free 16-byte row reads
 constexpr int OZ_A_STAGE = OZ_NS * OZ_BM * OZ_KS;   // 32 KB
 constexpr int OZ_B_STAGE = OZ_NS * OZ_BN * OZ_KS;   // 16 KB
@@ -436,8 +437,8 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
   if (uniform_count && *uniform_count != uniform_target) return;  // unequal weights: the FP64 weighted kernel handles it
   extern __shared__ __align__(1024) uint8_t oz_sm[];
   uint8_t* sA = oz_sm;
-  uint8_t* sB = oz_sm + OZ_STAGES * OZ_A_STAGE;
-  __shared__ __align__(8) uint64_t full[OZ_STAGES], empty[OZ_STAGES], acc_full, acc_empty;
+  uint8_t* sB = oz_sm + OZ_SYRK_STAGES * OZ_A_STAGE;
+  __shared__ __align__(8) uint64_t full[OZ_SYRK_STAGES], empty[OZ_SYRK_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
   __shared__ double scol[OZ_BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -459,7 +460,7 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
   };
 
   if (tid == 0) {
-    for (int s = 0; s < OZ_STAGES; ++s) {
+    for (int s = 0; s < OZ_SYRK_STAGES; ++s) {
       oz_mbar_init(&full[s], 1);
       oz_mbar_init(&empty[s], 1);
     }
@@ -493,7 +494,7 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
           for (int pp = 0; pp < 2 * OZ_NS; ++pp)  // (slice, plane) pieces: 64 rows x 16 bytes each
             oz_bulk_g2s(sB + stage * OZ_B_STAGE + pp * (OZ_BN * 16), b + (long)ks * OZ_A_STAGE + pp * (OZ_BM * 16),
                         OZ_BN * 16, &full[stage]);
-          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == OZ_SYRK_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -530,7 +531,7 @@ oz_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
             oz_commit(&empty[stage]);
           }
           __syncwarp();
-          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == OZ_SYRK_STAGES) { stage = 0; phase ^= 1; }
         }
         if (leader) oz_commit(&acc_full);
         __syncwarp();
@@ -605,7 +606,15 @@ extern "C" long npgp_rowquad_i8_workspace_bytes(int n, int M) {
 // T (n x M) = K (n x M) @ C (M x M, symmetric);  q[i] += sum_j T_ij K_ij (q zeroed by the caller; NULL to skip).
 // M must be a multiple of 64.  Replaces npgp_rowquad on the integer tensor-core path.
 static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
-                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice);
+                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice, bool gemm = true);
+
+// The slicing passes alone (K and C into `work`); follow with npgp_rowquad_i8_gemm_only.  Lets the caller put other
+// HBM-bound work on a second stream exactly under the tensor-core kernel.
+extern "C" int npgp_rowquad_i8_slice_only(int n, int M, const double* K, long ldk, const double* C, long ldc, void* work,
+                                          long work_bytes, cudaStream_t stream) {
+  if (!K || !C || !work) return (n == 0 || M == 0) ? NPGP_OK : NPGP_EINVAL;
+  return rowquad_i8_impl(n, M, K, ldk, C, ldc, const_cast<double*>(K), 2, nullptr, work, work_bytes, stream, true, false);
+}
 
 extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
                                double* q, void* work, long work_bytes, cudaStream_t stream) {
@@ -620,7 +629,7 @@ extern "C" int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk
 }
 
 static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
-                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice) {
+                           double* q, void* work, long work_bytes, cudaStream_t stream, bool slice, bool gemm) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (n == 0 || M == 0) return NPGP_OK;
   if (!K || !C || !T || !work) return NPGP_EINVAL;
@@ -637,6 +646,7 @@ static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double
     oz_slice_kernel<OZ_BN><<<(unsigned)(M / 8), 512, 0, stream>>>(M, M, M, C, ldc, Bs, eb);
     NPGP_LAUNCH_CHECK();
   }
+  if (!gemm) return NPGP_OK;
   static bool attr_set = false;
   if (!attr_set) {
     NPGP_CUDA(cudaFuncSetAttribute(oz_rowquad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
@@ -659,12 +669,15 @@ extern "C" long npgp_syrk_i8_workspace_bytes(int n, int M) {
 // The unweighted / equal-weights case of npgp_wsyrk on the integer tensor cores (exact Ozaki split).
 // uniform_count / uniform_target (optional): the kernel only runs when *uniform_count == uniform_target (device-side
 // gate, see npgp_wsyrk_hint); accumulate != 0: add to Out instead of overwriting it.
+// phase: 0 = slice K and run; 1 = slicing passes only (column maxima, exponents, transposed slices into `work`, so that
+// they can run on another stream under an unrelated kernel); 2 = tensor-core kernel only, on the slices a phase-1 call
+// with the same K left in `work`.
 extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev,
-                            const double* uniform_count, double uniform_target, int accumulate, double* Out, long ldo,
-                            void* work, long work_bytes, cudaStream_t stream) {
+                            const double* uniform_count, double uniform_target, int accumulate, int phase, double* Out,
+                            long ldo, void* work, long work_bytes, cudaStream_t stream) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
-  if (!Out || (n > 0 && !K) || !work) return NPGP_EINVAL;
+  if ((phase != 1 && !Out) || (n > 0 && !K) || !work || phase < 0 || phase > 2) return NPGP_EINVAL;
   if (M % OZ_BM) return NPGP_EUNSUPPORTED;
   if (work_bytes < npgp_syrk_i8_workspace_bytes(n, M)) return NPGP_EWORKSPACE;
   const long npad = ((long)n + OZ_KS - 1) / OZ_KS * OZ_KS;
@@ -672,10 +685,10 @@ extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ld
   int8_t* Xs = static_cast<int8_t*>(work);
   unsigned long long* cmax = reinterpret_cast<unsigned long long*>(Xs + npad * M * OZ_NS);
   int* ex = reinterpret_cast<int*>(cmax + M);
-  NPGP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned long long) * M, stream));
-  if (!accumulate) NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
+  if (phase != 1 && !accumulate) NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
   if (n == 0) return NPGP_OK;
-  {
+  if (phase != 2) {
+    NPGP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned long long) * M, stream));
     const int rows_per_cta = 256;
     dim3 grid(ceil_div(M, 256), ceil_div(n, rows_per_cta));
     oz_colmax_kernel<<<grid, 256, 0, stream>>>(n, M, K, ldk, rows_per_cta, cmax);
@@ -686,8 +699,9 @@ extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ld
     oz_slice_t_kernel<<<gs, 256, 0, stream>>>(n, M, K, ldk, ex, Xs);
     NPGP_LAUNCH_CHECK();
   }
+  if (phase == 1) return NPGP_OK;
   static bool attr_set = false;
-  constexpr int smem = OZ_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024;
+  constexpr int smem = OZ_SYRK_STAGES * (OZ_A_STAGE + OZ_B_STAGE) + 1024;
   if (!attr_set) {
     NPGP_CUDA(cudaFuncSetAttribute(oz_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;

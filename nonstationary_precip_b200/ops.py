@@ -167,9 +167,10 @@ def rowquad(K, Cm, need_q=True, T=None):
 _I8_WORK = {}
 
 
-def rowquad_i8(K, Cm, need_q=True, T=None):
+def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
     """rowquad on the integer tensor cores (tcgen05 kind::i8, exact Ozaki split, see csrc/ozaki.cu).  Cm must be
-    symmetric and M a multiple of 64.  The slice workspace is cached per (device, n, M)."""
+    symmetric and M a multiple of 64.  The slice workspace is cached per (device, n, M).  `between`: callable run after
+    the slicing passes have been enqueued and before the tensor-core kernel."""
     n, M = K.shape
     if T is None:
         T = torch.empty(n, M, dtype=torch.float64, device=K.device)
@@ -179,8 +180,15 @@ def rowquad_i8(K, Cm, need_q=True, T=None):
     work = _I8_WORK.get(key)
     if work is None:
         work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
-    check(lib().npgp_rowquad_i8(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q), ptr(work),
-                                nbytes, stream()), "npgp_rowquad_i8")
+    if between is None:
+        check(lib().npgp_rowquad_i8(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q),
+                                    ptr(work), nbytes, stream()), "npgp_rowquad_i8")
+    else:  # slicing passes, then `between()` (e.g. fork other HBM-bound work to a side stream), then the tensor-core kernel
+        check(lib().npgp_rowquad_i8_slice_only(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(work), nbytes,
+                                               stream()), "npgp_rowquad_i8_slice_only")
+        between()
+        check(lib().npgp_rowquad_i8_gemm_only(n, M, ptr(K), K.stride(0), ptr(T), T.stride(0), ptr(q), ptr(work), nbytes,
+                                              stream()), "npgp_rowquad_i8_gemm_only")
     return T, q
 
 
@@ -201,12 +209,21 @@ def syrk_i8(K, w0=None, alpha=1.0, out=None):
     if out is None:
         out = torch.empty(M, M, dtype=torch.float64, device=K.device)
     work, nbytes = _syrk_i8_work(K)
-    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), None, 0.0, 0, ptr(out), out.stride(0),
+    check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), None, 0.0, 0, 0, ptr(out), out.stride(0),
                              ptr(work), nbytes, stream()), "npgp_syrk_i8")
     return out
 
 
-def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None):
+def syrk_i8_prepare(K):
+    """Slicing passes of the int8 SYRK only (column maxima, exponents, transposed slices into the cached workspace): HBM
+    bound, meant to run on a side stream under a tensor-bound kernel.  Follow with wsyrk_i8(..., prepared=True)."""
+    n, M = K.shape
+    work, nbytes = _syrk_i8_work(K)
+    check(lib().npgp_syrk_i8(n, M, 1.0, ptr(K), K.stride(0), None, None, 0.0, 0, 1, None, 0, ptr(work), nbytes, stream()),
+          "npgp_syrk_i8(prepare)")
+
+
+def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None, prepared=False):
     """alpha * K^T diag(w) K with the device-side equal-weights gate of `wsyrk`: equal weights (the normal case of the
     SVGP step) run on the integer tensor cores, unequal ones on the FP64 weighted kernel; both are enqueued and the one
     the flag does not select exits at once."""
@@ -219,7 +236,7 @@ def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None):
           "npgp_wsyrk_weighted_only")
     work, nbytes = _syrk_i8_work(K)
     check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w), ptr(uniform_count), float(uniform_target), 1,
-                             ptr(out), out.stride(0), ptr(work), nbytes, stream()), "npgp_syrk_i8")
+                             2 if prepared else 0, ptr(out), out.stride(0), ptr(work), nbytes, stream()), "npgp_syrk_i8")
     return out
 
 

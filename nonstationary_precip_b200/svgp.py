@@ -290,8 +290,19 @@ class SVGPGibbs:
         # ---- data pass: K(X_B, Z) (+ mean), variance quadratic form, expected log-lik
         with self._sec("kxz_fwd"):
             K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
+        # the slicing passes of the int8 SYRK need only K: HBM bound, put on the second side stream exactly under the
+        # tensor-bound row-quadratic kernel (which leaves room for their CTAs on every SM)
+        i8_syrk = self.rowquad_impl == "i8" and M % 128 == 0 and hasattr(o, "wsyrk_i8")
+
+        def fork_syrk_slices():
+            with self._fork2():
+                o.syrk_i8_prepare(K)
+
         with self._sec("rowquad"):
-            T, q = self._rowquad(K, C)
+            if i8_syrk:
+                T, q = o.rowquad_i8(K, C, between=fork_syrk_slices)
+            else:
+                T, q = self._rowquad(K, C)
         acc, gmu, gv, _ = o.gauss_ell(yb, mu, q, s, noise, self.jitter_xx, 1e-6, 1.0 / Bg)
         ell = acc[0] / Bg
 
@@ -318,8 +329,9 @@ class SVGPGibbs:
                 du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
                 # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
-                if self.rowquad_impl == "i8" and M % 128 == 0 and hasattr(o, "wsyrk_i8"):
-                    dC = o.wsyrk_i8(K, gv, acc[2:3], float(Bl))
+                if i8_syrk:
+                    self._join2()
+                    dC = o.wsyrk_i8(K, gv, acc[2:3], float(Bl), prepared=True)
                 else:
                     dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
             if wsyrk_done is not None:
