@@ -27,6 +27,20 @@ def _softplus(x):
     return torch.nn.functional.softplus(x)
 
 
+def _syrk(Fc, out, use_i8=True):
+    """F^T F of a chunk: exact int8 tensor-core path when the width allows (multiple of 128), else FP64 DMMA."""
+    if use_i8 and Fc.shape[1] % 128 == 0 and Fc.is_contiguous():
+        return ops.syrk_i8(Fc, out=out)
+    return ops.wsyrk(Fc, out=out)
+
+
+def _rowmul(Fc, Csym, T, use_i8=True):
+    """T = F_chunk @ Csym (Csym symmetric) on the int8 tensor cores when the width allows (multiple of 64)."""
+    if use_i8 and Fc.shape[1] % 64 == 0 and Fc.is_contiguous():
+        return ops.rowquad_i8(Fc, Csym, need_q=False, T=T)
+    return ops.rowquad(Fc, Csym, need_q=False, T=T)
+
+
 def _inv_softplus(v: float) -> float:
     return v + math.log(-math.expm1(-v))
 
@@ -101,7 +115,7 @@ class SGPRGibbsStream(torch.nn.Module):
         for lo in range(0, n_loc, chunk):
             xc, yc = x[lo:lo + chunk].contiguous(), y[lo:lo + chunk].contiguous()
             _, K = self._chunk_forward(xc, ell_zd, alphad, Kbuf[:xc.shape[0]])
-            A += ops.wsyrk(K, out=Ac)
+            A += _syrk(K, Ac, getattr(self, 'use_i8', True))
             ops.colwsum(K, w=yc, out=b)
             yy += (yc * yc).sum()
         if all_reduce is not None:
@@ -139,7 +153,7 @@ class SGPRGibbsStream(torch.nn.Module):
         for lo in range(0, n_loc, chunk):
             xc, yc = x[lo:lo + chunk].contiguous(), y[lo:lo + chunk].contiguous()
             ell_x, K = self._chunk_forward(xc, ell_zd, alphad, Kbuf[:xc.shape[0]])
-            T, _ = ops.rowquad(K, dA2, need_q=False, T=Tbuf[:xc.shape[0]])
+            T, _ = _rowmul(K, dA2, Tbuf[:xc.shape[0]], getattr(self, 'use_i8', True))
             r = ops.gibbs_diag_bwd(xc, ell_x, self.Z.detach(), ell_zd, None, G=T, rowvec=yc, colvec=db,
                                    need_dx2=self.Z.requires_grad)
             d_ell_z += r["d_ell2"]
@@ -282,7 +296,7 @@ class SGPRSpatioTemporalStream(torch.nn.Module):
             Fc, Gc = Fbuf[:xc.shape[0]], Gbuf[:xc.shape[0]]
             self._chunk_features(xc, zs, zt, hypd, ell_zd, alphad, Fc)
             self._whiten(Fc, Gc, Ptd, Psd)
-            W += ops.wsyrk(Gc, out=Wc)
+            W += _syrk(Gc, Wc, getattr(self, 'use_i8', True))
             ops.colwsum(Gc, w=yc, out=c)
             yy += (yc * yc).sum()
         if all_reduce is not None:
@@ -327,7 +341,7 @@ class SGPRSpatioTemporalStream(torch.nn.Module):
             Fc, Gc, Tc = Fbuf[:xc.shape[0]], Gbuf[:xc.shape[0]], Tbuf[:xc.shape[0]]
             xt, xs, ell_x = self._chunk_features(xc, zs, zt, hypd, ell_zd, alphad, Fc)
             self._whiten(Fc, Gc, Ptd, Psd)
-            ops.rowquad(Gc, dW2, need_q=False, T=Tc)
+            _rowmul(Gc, dW2, Tc, getattr(self, 'use_i8', True))
             Tc.addcmul_(yc.unsqueeze(1), dc.unsqueeze(0))
             ops.dgemm(Tc[:, :M], Fc[:, :M], transA=True, beta=1.0, C=dPt)
             ops.dgemm(Tc[:, M:], Fc[:, M:], transA=True, beta=1.0, C=dPs)

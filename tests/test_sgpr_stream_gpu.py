@@ -15,7 +15,7 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
 
 
-@pytest.mark.parametrize("n,M,D,chunk", [(700, 48, 2, 256), (1000, 130, 3, 333)])
+@pytest.mark.parametrize("n,M,D,chunk", [(700, 48, 2, 256), (1000, 130, 3, 333), (1500, 128, 2, 512)])  # M = 128: int8 GEMMs
 def test_streamed_sgpr_matches_dense_oracle(n, M, D, chunk):
     from nonstationary_precip_b200.sgpr import SGPRGibbsStream, _inv_softplus
     g = torch.Generator().manual_seed(n)
@@ -86,7 +86,7 @@ def test_streamed_sgpr_rank_sharding_by_emulated_all_reduce():
     assert rel(r0.Z.grad, full.Z.grad) < 1e-8
 
 
-@pytest.mark.parametrize("n,M,chunk", [(500, 24, 192), (900, 40, 900)])
+@pytest.mark.parametrize("n,M,chunk", [(500, 24, 192), (900, 40, 900), (1200, 64, 512)])  # 2M = 128: int8 GEMMs
 def test_streamed_spatio_temporal_sgpr_matches_dense_oracle(n, M, chunk):
     """Config-3 model (Nystrom RBF x Periodic on time + scaled Nystrom Gibbs on lon/lat, one inducing set) evaluated
     matrix free, against the oracle's dense rank-2M bound (spatio_temporal_models.py:35-60)."""
@@ -97,10 +97,19 @@ def test_streamed_spatio_temporal_sgpr_matches_dense_oracle(n, M, chunk):
     Z = x[torch.randperm(n, generator=g)[:M]].clone()
     le = math.log(0.4) + 0.2 * torch.randn(2, M, generator=g)
     c, os_, lam = torch.full((2,), math.log(0.4)), torch.ones(2), torch.full((2, 2), 1.3)
-    hyp0 = (0.9, 1.3, 1.7, 7.6)
+    # 64 inducing times under a smooth kernel make the temporal Kzz numerically singular (jitter ladder, objective
+    # sensitive at cond * eps); the larger case uses a shorter temporal lengthscale so that the comparison stays sharp
+    hyp0 = (0.9, 1.3, 1.7, 7.6) if M < 64 else (0.12, 0.8, 1.7, 7.6)
     model = SGPRSpatioTemporalStream(Z.cuda(), le.cuda(), c.cuda(), os_.cuda(), lam.cuda(), hyp_t=hyp0,
                                      outputscale_s=0.8, noise=0.05)
     loss = model.neg_objective_and_grad(x.cuda(), y.cuda(), chunk=chunk)
+    if (2 * M) % 128 == 0:  # this case ran on the int8 tensor-core GEMMs: the FP64 DMMA path must give the same numbers
+        ref = SGPRSpatioTemporalStream(Z.cuda(), le.cuda(), c.cuda(), os_.cuda(), lam.cuda(), hyp_t=hyp0,
+                                       outputscale_s=0.8, noise=0.05)
+        ref.use_i8 = False
+        loss_ref = ref.neg_objective_and_grad(x.cuda(), y.cuda(), chunk=chunk)
+        assert abs(loss.item() - loss_ref.item()) < 1e-12 * abs(loss_ref.item())
+        assert rel(model.raw_hyp_t.grad, ref.raw_hyp_t.grad) < 1e-7 and rel(model.Z.grad, ref.Z.grad) < 1e-7
 
     Zc, lec = Z.clone().requires_grad_(True), le.clone().requires_grad_(True)
     raw = torch.tensor([_inv_softplus(hyp0[0]), _inv_softplus(hyp0[1]), _inv_softplus(hyp0[2]),
@@ -113,7 +122,8 @@ def test_streamed_spatio_temporal_sgpr_matches_dense_oracle(n, M, chunk):
     Zo = torch.cat([Zc[:, :1].detach(), Zc[:, 1:]], 1)
     want = -o.st_sgpr_objective(x, y, Zo, lec, hyp, o.softplus(ro), 1e-4 + o.softplus(rn), c, os_, lam)
     want.backward()
-    assert abs(loss.item() - want.item()) < 1e-8 * abs(want.item())
+    # (with 64 inducing times the Cholesky factors of the two implementations already differ at 1e-8 of the objective)
+    assert abs(loss.item() - want.item()) < (1e-8 if M < 64 else 1e-6) * abs(want.item())
     assert rel(model.log_ell_z.grad, lec.grad) < 1e-5
     assert rel(model.Z.grad, Zc.grad) < 1e-5
     assert float(model.Z.grad[:, 0].abs().max()) == 0.0
