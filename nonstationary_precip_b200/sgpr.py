@@ -3,13 +3,17 @@
 evaluated WITHOUT materialising the N x M root, so that it runs at the scale of BASELINE config 3 (N = 4M rows,
 M = 2048), where the reference's `k_ux1.matmul(inv_root)` would need 68 GB.
 
-With K = Gibbs(X, Z) (unscaled, rows streamed in chunks) the bound depends on the rows only through
-    A = K^T K (M x M, DMMA SYRK),   b = K^T y,   y^T y
-(the root R = K U^-1 of the reference satisfies R^T R = U^-T A U^-1), so one pass over the rows accumulates just those.  Everything else is
-M x M algebra on the blocked Cholesky / GEMM kernels (differentiated by the autograd Functions of `functional.py`).
-The data-side gradient needs a second pass:  dObj/dK_chunk = K_chunk (dA + dA^T) + y_chunk db^T, formed by one DMMA GEMM
-per chunk and consumed inside the analytic Gibbs backward kernel (never stored as a gradient matrix); the lengthscale
-field is interpolated matrix free in both passes.  Rows shard over ranks: A, b, y^T y and the gradients are sums."""
+With K = Gibbs(X, Z) (unscaled, rows streamed in chunks) and the root rows G = K L^-T (Kzz = L L^T) the bound depends on
+the rows only through
+    W = G^T G (M x M SYRK),   c = G^T y,   y^T y,
+so one pass over the rows accumulates just those (each chunk is whitened by a triangular GEMM first: accumulating the
+unwhitened K^T K is cheaper but numerically unusable at N ~ 1e6, see neg_objective_and_grad).  Everything else is M x M
+algebra on the blocked Cholesky / GEMM kernels (differentiated by the autograd Functions of `functional.py`).  The
+data-side gradient needs a second pass: dObj/dG_chunk = G_chunk (dW + dW^T) + y_chunk dc^T, pushed back through the
+whitening (dK = dG L^-1, dL^-1 += dG^T K) and consumed inside the analytic Gibbs backward kernel (never stored as a
+gradient matrix); the lengthscale field is interpolated matrix free in both passes.  Rows shard over ranks: W, c, y^T y
+and the gradients are sums.  The large products run on the int8 tensor cores (exact Ozaki split, csrc/ozaki.cu) when M
+is a multiple of 128, on the FP64 tensor pipe otherwise."""
 from __future__ import annotations
 
 import math
@@ -98,87 +102,100 @@ class SGPRGibbsStream(torch.nn.Module):
                                world_size: int = 1):
         """Fills .grad of the parameters with the gradient of MINUS the collapsed SGPR objective (divided by n, as
         ExactMarginalLogLikelihood does) and returns its value.  `x`, `y`: this rank's rows; `n_total`: global row count;
-        `all_reduce(t)` sums a tensor over ranks (A, b, y^T y after pass 1; the flat gradient after pass 2)."""
+        `all_reduce(t)` sums a tensor over ranks (W, c, y^T y after pass 1; the data-side gradients after pass 2).
+
+        Rows are whitened chunk by chunk before they are accumulated, G = K L^-T (the reference's own root,
+        gibbs_kernels.py:225), so that B = I + (s/noise) G^T G has eigenvalues >= 1 and log det Kzz cancels: accumulating
+        the unwhitened Gram matrix K^T K instead (12 instead of 22 M^2 flop per row) was measured to move the objective by
+        4e-5 at N = 4.2e6 when K^T K changed in its last bits -- `Kzz + (s/noise) K^T K` is too ill-conditioned there."""
         dev = x.device
         n_loc = x.shape[0]
         n = n_total if n_total is not None else n_loc
         M, D = self.Z.shape
-        ell_z, alpha, (Kzz, L, P), lp = self._z_side()
-        ell_zd, alphad = ell_z.detach().contiguous(), alpha.detach().contiguous()
+        use_i8 = getattr(self, "use_i8", True)
+        ell_z, alpha, (_, _, P), lp = self._z_side()
+        ell_zd, alphad, Pd = ell_z.detach().contiguous(), alpha.detach().contiguous(), P.detach()
 
-        # ---- pass 1: A = K^T K, b = K^T y, y^T y
-        A = torch.zeros(M, M, dtype=torch.float64, device=dev)
-        b = torch.zeros(M, dtype=torch.float64, device=dev)
+        # ---- pass 1: W = G^T G, c = G^T y, y^T y
+        W = torch.zeros(M, M, dtype=torch.float64, device=dev)
+        c = torch.zeros(M, dtype=torch.float64, device=dev)
         yy = torch.zeros((), dtype=torch.float64, device=dev)
-        Kbuf = torch.empty(min(chunk, n_loc), M, dtype=torch.float64, device=dev)
-        Ac = torch.empty_like(A)
+        rows = min(chunk, n_loc)
+        Kbuf = torch.empty(rows, M, dtype=torch.float64, device=dev)
+        Gbuf = torch.empty_like(Kbuf)
+        Wc = torch.empty_like(W)
         for lo in range(0, n_loc, chunk):
             xc, yc = x[lo:lo + chunk].contiguous(), y[lo:lo + chunk].contiguous()
             _, K = self._chunk_forward(xc, ell_zd, alphad, Kbuf[:xc.shape[0]])
-            A += _syrk(K, Ac, getattr(self, 'use_i8', True))
-            ops.colwsum(K, w=yc, out=b)
+            G = ops.dgemm(K, Pd, transB=True, tri_b=2, C=Gbuf[:xc.shape[0]])
+            W += _syrk(G, Wc, use_i8)
+            ops.colwsum(G, w=yc, out=c)
             yy += (yc * yc).sum()
         if all_reduce is not None:
-            packed = torch.cat([A.reshape(-1), b, yy.reshape(1)])
+            packed = torch.cat([W.reshape(-1), c, yy.reshape(1)])
             all_reduce(packed)
-            A, b, yy = packed[:M * M].reshape(M, M), packed[M * M:M * M + M], packed[-1]
-        A = A.clone().requires_grad_(True)
-        b = b.clone().requires_grad_(True)
+            W, c, yy = packed[:M * M].reshape(M, M), packed[M * M:M * M + M], packed[-1]
+        W = W.clone().requires_grad_(True)
+        c = c.clone().requires_grad_(True)
 
-        # ---- M x M algebra (autograd over the Cholesky / GEMM kernels)
+        # ---- M x M algebra: B = I + (s/noise) W
         s = _softplus(self.raw_outputscale).reshape(())
         noise = (1e-4 + _softplus(self.raw_noise)).reshape(())
-        # Numerically stable form: with Sigma = Kzz + (s/noise) A (positive definite by construction),
-        #   log det(s Q + noise I) = n log noise + log det Sigma - log det Kzz,
-        #   y^T (s Q + noise I)^-1 y = y^T y / noise - (s / noise^2) b^T Sigma^-1 b,     Q = K Kzz^-1 K^T.
-        # (Forming I + (s/noise) P A P^T instead loses positive definiteness for ill-conditioned Kzz.)
-        Sigma = Kzz + (s / noise) * (0.5 * (A + A.T))
-        LS, PS = F.psd_safe_chol_inv(Sigma)
-        w = F.matmul(PS, b)
+        Bm = torch.eye(M, dtype=torch.float64, device=dev) + (s / noise) * (0.5 * (W + W.T))
+        LB, PB = F.psd_safe_chol_inv(Bm)
+        w = F.matmul(PB, c)
         quad = yy / noise - (s / (noise * noise)) * (w * w).sum()
-        logdet = 2.0 * (torch.log(torch.diagonal(LS)).sum() - torch.log(torch.diagonal(L)).sum()) + n * torch.log(noise)
+        logdet = 2.0 * torch.log(torch.diagonal(LB)).sum() + n * torch.log(noise)
         ll = -0.5 * (quad + logdet + n * LOG2PI)
-        trace = -0.5 * (n - (F.matmul(P, A) * P).sum()) / noise  # tr(Kzz^-1 A) = tr(P A P^T)
+        trace = -0.5 * (n - torch.diagonal(W).sum()) / noise  # unscaled kernel (gibbs_kernels.py:256-260)
         obj = (ll + trace + lp) / n
         loss = -obj
-        dA, db = torch.autograd.grad(loss, [A, b], retain_graph=True)
-        dA2 = (dA + dA.T).contiguous()  # d(loss)/dK_chunk = K_chunk (dA + dA^T) + y db^T
-        db = db.contiguous()
+        dW, dc = torch.autograd.grad(loss, [W, c], retain_graph=True)
+        dW2 = (dW + dW.T).contiguous()
+        dc = dc.contiguous()
 
-        # ---- pass 2: data-side gradients, streamed
+        # ---- pass 2: dG = G (dW + dW^T) + y dc^T;  dK = dG P (to the analytic Gibbs backward);  dP += dG^T K
         d_ell_z = torch.zeros_like(ell_zd)
         dZ = torch.zeros_like(self.Z)
         dalpha = torch.zeros(D, M, 1, dtype=torch.float64, device=dev)
+        dP = torch.zeros(M, M, dtype=torch.float64, device=dev)
         Tbuf = torch.empty_like(Kbuf)
+        need_dz = self.Z.requires_grad
         for lo in range(0, n_loc, chunk):
             xc, yc = x[lo:lo + chunk].contiguous(), y[lo:lo + chunk].contiguous()
             ell_x, K = self._chunk_forward(xc, ell_zd, alphad, Kbuf[:xc.shape[0]])
-            T, _ = _rowmul(K, dA2, Tbuf[:xc.shape[0]], getattr(self, 'use_i8', True))
-            r = ops.gibbs_diag_bwd(xc, ell_x, self.Z.detach(), ell_zd, None, G=T, rowvec=yc, colvec=db,
-                                   need_dx2=self.Z.requires_grad)
+            G = ops.dgemm(K, Pd, transB=True, tri_b=2, C=Gbuf[:xc.shape[0]])
+            T, _ = _rowmul(G, dW2, Tbuf[:xc.shape[0]], use_i8)
+            T.addcmul_(yc.unsqueeze(1), dc.unsqueeze(0))
+            ops.dgemm(T, K, transA=True, beta=1.0, C=dP)
+            dK = ops.dgemm(T, Pd, tri_b=1, C=Gbuf[:xc.shape[0]])  # G is no longer needed: reuse its storage
+            r = ops.gibbs_diag_bwd(xc, ell_x, self.Z.detach(), ell_zd, None, G=dK, need_dx2=need_dz)
             d_ell_z += r["d_ell2"]
-            if self.Z.requires_grad:
+            if need_dz:
                 dZ += r["d_x2"]
             dlog = (r["d_ell1"] * ell_x).unsqueeze(-1)
             da, dzf = ops.rbf_matvec_bwd(xc, self.Z.detach(), self.prior_lam, self.prior_os, alphad.unsqueeze(-1), dlog,
-                                         need_dz=self.Z.requires_grad)
+                                         need_dz=need_dz)
             dalpha += da
-            if self.Z.requires_grad:
+            if need_dz:
                 dZ += dzf
         if all_reduce is not None:
-            packed = torch.cat([d_ell_z.reshape(-1), dZ.reshape(-1), dalpha.reshape(-1)])
+            parts = [d_ell_z, dZ, dalpha, dP]
+            packed = torch.cat([t.reshape(-1) for t in parts])
             all_reduce(packed)
-            k1, k2 = d_ell_z.numel(), dZ.numel()
-            d_ell_z, dZ, dalpha = (packed[:k1].reshape(d_ell_z.shape), packed[k1:k1 + k2].reshape(dZ.shape),
-                                   packed[k1 + k2:].reshape(dalpha.shape))
+            out, off = [], 0
+            for t in parts:
+                out.append(packed[off:off + t.numel()].reshape(t.shape))
+                off += t.numel()
+            d_ell_z, dZ, dalpha, dP = out
 
-        # ---- finish: Z-side graph (Kzz, prior, alpha) + the streamed contributions
+        # ---- finish: Z-side graph (Kzz -> P, prior, alpha) + the streamed contributions
         for p_ in self.parameters():
             p_.grad = None
-        torch.autograd.backward([loss, alpha], [torch.ones_like(loss), dalpha.squeeze(-1)])
+        torch.autograd.backward([loss, alpha, P], [torch.ones_like(loss), dalpha.squeeze(-1), torch.tril(dP)])
         with torch.no_grad():
             self.log_ell_z.grad += d_ell_z * ell_zd
-            if self.Z.requires_grad:
+            if need_dz:
                 self.Z.grad += dZ
         return loss.detach()
 

@@ -111,9 +111,9 @@ def c3():
     xs, ys = x[rank * n_loc:(rank + 1) * n_loc], y[rank * n_loc:(rank + 1) * n_loc]
     best, med = ev_time(lambda: model.neg_objective_and_grad(xs, ys, chunk=65536, n_total=N), iters=2, warm=1)
     loss = model.neg_objective_and_grad(xs, ys, chunk=65536, n_total=N).item()
-    flop = 3.0 * n_loc * M * M  # SYRK (N M^2) + second-pass GEMM (2 N M^2)
+    flop = 22.0 * n_loc * M * M  # whitening 2+2, SYRK 4, dG 8, dK 2, dP 4 (x n M^2); FP64-equivalent (int8 GEMMs inside)
     print(json.dumps({"config": "c3 (spatial Gibbs part) streamed SGPR objective+grad, N=%d, M=%d, rows on this rank %d" % (
-        N, M, n_loc), "ms_per_eval": best, "evals_per_s": 1e3 / best, "tflops_3NM2": flop / best / 1e9, "loss": loss,
+        N, M, n_loc), "ms_per_eval": best, "evals_per_s": 1e3 / best, "fp64_equiv_tflops_22NM2": flop / best / 1e9, "loss": loss,
         "finite_grads": bool(all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)),
         "max_mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
 
