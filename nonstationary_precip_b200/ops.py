@@ -164,7 +164,17 @@ def rowquad(K, Cm, need_q=True, T=None):
     return T, q
 
 
-_I8_WORK = {}
+_I8_WORK = {}  # slice workspaces of the int8 GEMMs, keyed by shape; a handful of shapes recur (minibatch, last chunk)
+_I8_WORK_MAX = 6
+
+
+def _i8_work(key, nbytes, device):
+    work = _I8_WORK.get(key)
+    if work is None:
+        while len(_I8_WORK) >= _I8_WORK_MAX:  # drop the oldest entry (dict preserves insertion order)
+            _I8_WORK.pop(next(iter(_I8_WORK)))
+        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=device)  # raw bytes
+    return work
 
 
 def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
@@ -176,10 +186,7 @@ def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
         T = torch.empty(n, M, dtype=torch.float64, device=K.device)
     q = torch.zeros(n, dtype=torch.float64, device=K.device) if need_q else None
     nbytes = lib().npgp_rowquad_i8_workspace_bytes(n, M)
-    key = (K.device.index, n, M)
-    work = _I8_WORK.get(key)
-    if work is None:
-        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
+    work = _i8_work((K.device.index, n, M), nbytes, K.device)
     if between is None:
         check(lib().npgp_rowquad_i8(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q),
                                     ptr(work), nbytes, stream()), "npgp_rowquad_i8")
@@ -195,11 +202,7 @@ def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
 def _syrk_i8_work(K):
     n, M = K.shape
     nbytes = lib().npgp_syrk_i8_workspace_bytes(n, M)
-    key = ("syrk", K.device.index, n, M)
-    work = _I8_WORK.get(key)
-    if work is None:
-        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=K.device)  # raw bytes
-    return work, nbytes
+    return _i8_work(("syrk", K.device.index, n, M), nbytes, K.device), nbytes
 
 
 def syrk_i8(K, w0=None, alpha=1.0, out=None):

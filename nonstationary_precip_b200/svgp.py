@@ -465,6 +465,8 @@ class SVGPGibbs:
             self.loss_and_grad(self._gx, self._gy, world_size, B_global)
             if world_size == 1:
                 self.adam_step(lr)
+        # the graph holds raw pointers into the cached slice workspaces of the int8 GEMMs: keep them alive with the graph
+        self._graph_keepalive = list(getattr(self.o, "_I8_WORK", {}).values())
         for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
             t.copy_(s)
         self.step_count = int(self.step_dev.item())

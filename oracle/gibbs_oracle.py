@@ -95,7 +95,8 @@ def field_interp_diag(x, Zg, ell_g, c, os, lam, jitter: float = 1e-4) -> torch.T
     Kgg = rbf_ard_K(Zg, Zg, lam, os) + jitter * torch.eye(Zg.shape[0], dtype=x.dtype)
     Kxg = rbf_ard_K(x, Zg, lam, os)  # (D,n,m)
     rhs = torch.log(ell_g) - c.unsqueeze(-1)
-    alpha = torch.linalg.solve(Kgg, rhs.unsqueeze(-1)).squeeze(-1)  # (D,m)
+    # one LU solve per dimension: the batched call hits an MKL DLASWP failure (and then hangs) at m = 1024 in this build
+    alpha = torch.stack([torch.linalg.solve(Kgg[d], rhs[d].unsqueeze(-1)).squeeze(-1) for d in range(rhs.shape[0])])  # (D,m)
     mu = c.unsqueeze(-1) + (Kxg * alpha.unsqueeze(-2)).sum(-1)
     return torch.exp(mu)
 
