@@ -633,7 +633,10 @@ static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (n == 0 || M == 0) return NPGP_OK;
   if (!K || !C || !T || !work) return NPGP_EINVAL;
-  if (M % OZ_BN || (ldt & 1) || (reinterpret_cast<uintptr_t>(T) & 15)) return NPGP_EUNSUPPORTED;
+  // 16-byte vector accesses: T rows, the K tile of the row dot and the slicers' reads of K and C
+  if (M % OZ_BN || (ldt & 1) || (reinterpret_cast<uintptr_t>(T) & 15) || (ldk & 1) ||
+      (reinterpret_cast<uintptr_t>(K) & 15) || (slice && ((ldc & 1) || (reinterpret_cast<uintptr_t>(C) & 15))))
+    return NPGP_EUNSUPPORTED;
   if (work_bytes < npgp_rowquad_i8_workspace_bytes(n, M)) return NPGP_EWORKSPACE;
   const long npad = ((long)n + OZ_BM - 1) / OZ_BM * OZ_BM;
   int8_t* As = static_cast<int8_t*>(work);

@@ -44,3 +44,20 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.npgp_gibbs_diag_fwd(2, -1, 4, None, None, None, None, None, None, 4, None, None, None) == -1
     assert lib.npgp_potrf_workspace_bytes(1024) > 8 * 1024 * 1024
     assert lib.npgp_set_gemm_config(99) == -1
+
+
+def test_int8_gemm_argument_errors_without_a_gpu():
+    """npgp_rowquad_i8 / npgp_syrk_i8 validate shapes, alignment and workspace before any launch."""
+    from nonstationary_precip_b200 import _lib
+    lib = _lib.lib()
+    a = 4096  # fake, 16-byte aligned device addresses: the calls below must return before touching them
+    assert lib.npgp_rowquad_i8_workspace_bytes(65536, 1024) >= 65536 * 1024 * 8 + 1024 * 1024 * 8
+    assert lib.npgp_rowquad_i8(10, 48, a, 48, a, 48, a, 48, None, a, 1 << 40, None) == -2     # M % 64 != 0
+    assert lib.npgp_rowquad_i8(10, 64, a, 63, a, 64, a, 64, None, a, 1 << 40, None) == -2     # odd ldk
+    assert lib.npgp_rowquad_i8(10, 64, a + 8, 64, a, 64, a, 64, None, a, 1 << 40, None) == -2  # K not 16-byte aligned
+    assert lib.npgp_rowquad_i8(10, 64, a, 64, a, 64, a, 64, None, a, 16, None) == -3           # workspace too small
+    assert lib.npgp_rowquad_i8(10, 64, None, 64, a, 64, a, 64, None, a, 1 << 40, None) == -1   # NULL operand
+    assert lib.npgp_rowquad_i8(0, 64, None, 64, None, 64, None, 64, None, None, 0, None) == 0  # empty: nothing to do
+    assert lib.npgp_syrk_i8(10, 192, 1.0, a, 192, None, None, 0.0, 0, 0, a, 192, a, 1 << 40, None) == -2  # M % 128 != 0
+    assert lib.npgp_syrk_i8(10, 128, 1.0, a, 128, None, None, 0.0, 0, 7, a, 128, a, 1 << 40, None) == -1  # bad phase
+    assert lib.npgp_syrk_i8(10, 128, 1.0, a, 128, None, None, 0.0, 0, 0, a, 128, a, 16, None) == -3
