@@ -174,6 +174,8 @@ long npgp_syrk_i8_workspace_bytes(int n, int M);
 int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, const double* uniform_count,
                  double uniform_target, int accumulate, int phase, double* Out, long ldo, void* work, long work_bytes,
                  npgp_stream_t stream); /* phase: 0 slice + run, 1 slicing passes only, 2 run on the slices left in work */
+int npgp_syrk_i8_prepare(int n, int M, const double* K, long ldk, const double* w, double* wsum, void* work,
+                         long work_bytes, npgp_stream_t stream); /* phase 1 + fused wsum[j] = sum_i w_i K_ij (w, wsum may be NULL) */
 int npgp_wsyrk_weighted_only(int n, int M, double alpha, const double* K, long ldk, const double* w,
                              const double* uniform_count, double uniform_target, double* Out, long ldo,
                              npgp_stream_t stream);

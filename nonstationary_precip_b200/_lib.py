@@ -36,6 +36,7 @@ _SIGS = {
     "npgp_rowquad_i8_gemm_only": ([_i, _i, _p, _l, _p, _l, _p, _p, _l, _p], _i),
     "npgp_syrk_i8_workspace_bytes": ([_i, _i], _l),
     "npgp_syrk_i8": ([_i, _i, _d, _p, _l, _p, _p, _d, _i, _i, _p, _l, _p, _l, _p], _i),
+    "npgp_syrk_i8_prepare": ([_i, _i, _p, _l, _p, _p, _p, _l, _p], _i),
     "npgp_wsyrk_weighted_only": ([_i, _i, _d, _p, _l, _p, _p, _d, _p, _l, _p], _i),
     "npgp_rowquad_i8": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _p], _i),
     "npgp_wsyrk": ([_i, _i, _d, _p, _l, _p, _p, _l, _p], _i),

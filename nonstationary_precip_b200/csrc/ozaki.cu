@@ -134,13 +134,25 @@ __global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, 
 }
 
 // Column maxima of |X| (R x Kd) as int64 bit patterns (non-negative doubles order like integers); cmax zeroed by the caller.
+// Optionally the same pass also accumulates the weighted column sums wsum[j] += sum_i w_i X_ij (K^T g_mu of the SVGP step,
+// which would otherwise be one more read of X).
 __global__ void __launch_bounds__(256) oz_colmax_kernel(int R, int Kd, const double* __restrict__ X, long ldx,
-                                                        int rows_per_cta, unsigned long long* __restrict__ cmax) {
+                                                        int rows_per_cta, unsigned long long* __restrict__ cmax,
+                                                        const double* __restrict__ w, double* __restrict__ wsum) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= Kd) return;
   const int i0 = blockIdx.y * rows_per_cta, i1 = min(R, i0 + rows_per_cta);
-  double m = 0.0;
-  for (int i = i0; i < i1; ++i) m = fmax(m, fabs(X[(long)i * ldx + j]));
+  double m = 0.0, acc = 0.0;
+  if (w) {
+    for (int i = i0; i < i1; ++i) {
+      const double v = X[(long)i * ldx + j];
+      m = fmax(m, fabs(v));
+      acc = fma(w[i], v, acc);
+    }
+    atomicAdd(&wsum[j], acc);
+  } else {
+    for (int i = i0; i < i1; ++i) m = fmax(m, fabs(X[(long)i * ldx + j]));
+  }
   atomicMax(&cmax[j], (unsigned long long)__double_as_longlong(m));
 }
 
@@ -675,9 +687,28 @@ extern "C" long npgp_syrk_i8_workspace_bytes(int n, int M) {
 // phase: 0 = slice K and run; 1 = slicing passes only (column maxima, exponents, transposed slices into `work`, so that
 // they can run on another stream under an unrelated kernel); 2 = tensor-core kernel only, on the slices a phase-1 call
 // with the same K left in `work`.
+static int syrk_i8_impl(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev,
+                        const double* uniform_count, double uniform_target, int accumulate, int phase, double* Out,
+                        long ldo, void* work, long work_bytes, const double* colw, double* colwsum, cudaStream_t stream);
+
 extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev,
                             const double* uniform_count, double uniform_target, int accumulate, int phase, double* Out,
                             long ldo, void* work, long work_bytes, cudaStream_t stream) {
+  return syrk_i8_impl(n, M, alpha, K, ldk, w0_dev, uniform_count, uniform_target, accumulate, phase, Out, ldo, work,
+                      work_bytes, nullptr, nullptr, stream);
+}
+
+// The slicing passes of npgp_syrk_i8 (phase 1) with the weighted column sums wsum[j] = sum_i w_i K_ij (overwritten) fused
+// into the column-maximum pass: the SVGP step gets K^T g_mu from the read of K it needs anyway.
+extern "C" int npgp_syrk_i8_prepare(int n, int M, const double* K, long ldk, const double* w, double* wsum, void* work,
+                                    long work_bytes, cudaStream_t stream) {
+  if ((w == nullptr) != (wsum == nullptr)) return NPGP_EINVAL;
+  return syrk_i8_impl(n, M, 1.0, K, ldk, nullptr, nullptr, 0.0, 0, 1, nullptr, 0, work, work_bytes, w, wsum, stream);
+}
+
+static int syrk_i8_impl(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev,
+                        const double* uniform_count, double uniform_target, int accumulate, int phase, double* Out,
+                        long ldo, void* work, long work_bytes, const double* colw, double* colwsum, cudaStream_t stream) {
   if (n < 0 || M < 0) return NPGP_EINVAL;
   if (M == 0) return NPGP_OK;
   if ((phase != 1 && !Out) || (n > 0 && !K) || !work || phase < 0 || phase > 2) return NPGP_EINVAL;
@@ -689,12 +720,13 @@ extern "C" int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ld
   unsigned long long* cmax = reinterpret_cast<unsigned long long*>(Xs + npad * M * OZ_NS);
   int* ex = reinterpret_cast<int*>(cmax + M);
   if (phase != 1 && !accumulate) NPGP_CUDA(cudaMemset2DAsync(Out, sizeof(double) * ldo, 0, sizeof(double) * M, M, stream));
+  if (colwsum) NPGP_CUDA(cudaMemsetAsync(colwsum, 0, sizeof(double) * M, stream));
   if (n == 0) return NPGP_OK;
   if (phase != 2) {
     NPGP_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned long long) * M, stream));
     const int rows_per_cta = 256;
     dim3 grid(ceil_div(M, 256), ceil_div(n, rows_per_cta));
-    oz_colmax_kernel<<<grid, 256, 0, stream>>>(n, M, K, ldk, rows_per_cta, cmax);
+    oz_colmax_kernel<<<grid, 256, 0, stream>>>(n, M, K, ldk, rows_per_cta, cmax, colw, colwsum);
     NPGP_LAUNCH_CHECK();
     oz_exp_from_max_kernel<<<ceil_div(M, 256), 256, 0, stream>>>(M, cmax, ex);
     NPGP_LAUNCH_CHECK();

@@ -217,13 +217,16 @@ def syrk_i8(K, w0=None, alpha=1.0, out=None):
     return out
 
 
-def syrk_i8_prepare(K):
+def syrk_i8_prepare(K, w=None):
     """Slicing passes of the int8 SYRK only (column maxima, exponents, transposed slices into the cached workspace): HBM
-    bound, meant to run on a side stream under a tensor-bound kernel.  Follow with wsyrk_i8(..., prepared=True)."""
+    bound, meant to run on a side stream under a tensor-bound kernel.  Follow with wsyrk_i8(..., prepared=True).  With
+    `w` (n,) the column-maximum pass also returns K^T w (M,), saving a separate pass over K."""
     n, M = K.shape
     work, nbytes = _syrk_i8_work(K)
-    check(lib().npgp_syrk_i8(n, M, 1.0, ptr(K), K.stride(0), None, None, 0.0, 0, 1, None, 0, ptr(work), nbytes, stream()),
-          "npgp_syrk_i8(prepare)")
+    wsum = torch.empty(M, dtype=torch.float64, device=K.device) if w is not None else None
+    check(lib().npgp_syrk_i8_prepare(n, M, ptr(K), K.stride(0), ptr(_c(w)), ptr(wsum), ptr(work), nbytes, stream()),
+          "npgp_syrk_i8_prepare")
+    return wsum
 
 
 def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None, prepared=False):

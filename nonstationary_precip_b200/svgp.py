@@ -294,9 +294,13 @@ class SVGPGibbs:
         # tensor-bound row-quadratic kernel (which leaves room for their CTAs on every SM)
         i8_syrk = self.rowquad_impl == "i8" and M % 128 == 0 and hasattr(o, "wsyrk_i8")
 
+        du_box = []
+
         def fork_syrk_slices():
+            # d(ELL)/d(mu) does not depend on the variance, so K^T g_mu rides on the column-maximum pass of the slicing
+            gmu_early = ((1.0 / Bg) * (yb - mu)) / noise
             with self._fork2():
-                o.syrk_i8_prepare(K)
+                du_box.append(o.syrk_i8_prepare(K, gmu_early))
 
         with self._sec("rowquad"):
             if i8_syrk:
@@ -325,12 +329,15 @@ class SVGPGibbs:
         # backward on the main stream, which starts when the SYRK has finished.
         wsyrk_done = torch.cuda.Event() if (self._side is not None and self.overlap) else None
         with self._fork():
-            with self._sec("colwsum"):
-                du = o.colwsum(K, w=gmu)
+            if i8_syrk:
+                self._join2()
+                du = du_box[0]
+            else:
+                with self._sec("colwsum"):
+                    du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
                 # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
                 if i8_syrk:
-                    self._join2()
                     dC = o.wsyrk_i8(K, gv, acc[2:3], float(Bl), prepared=True)
                 else:
                     dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
