@@ -1,10 +1,13 @@
-// Exact-integer (Ozaki-split) evaluation of the row-quadratic contraction  T = K C,  q_i = sum_j T_ij K_ij  on the
-// 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), as an alternative to the FP64 DMMA GEMM of
-// dgemm.cu (B200 has no FP64 tcgen05 kind and DMMA peaks at 37 TFLOP/s).
+// Exact-integer (Ozaki-split) evaluation of the two large contractions of the sparse-GP objectives,
+//     row-quadratic:  T = K C,  q_i = sum_j T_ij K_ij            (npgp_rowquad_i8)
+//     SYRK:           Out = alpha w0 K^T K                        (npgp_syrk_i8)
+// on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), as an alternative to the FP64 DMMA
+// GEMM of dgemm.cu (B200 has no FP64 tcgen05 kind and DMMA peaks at 37 TFLOP/s).  Measured at B = 65536, M = 1024:
+// 1.95 ms against 4.03 ms (row-quadratic) and 1.05 ms against 2.14 ms (SYRK), results equal to FP64 rounding.
 //
 // Arithmetic.  Every row i of K and every row j of C (C is symmetric: row j = column j) is scaled by a power of two so
 // that its entries lie in [-1, 1] and split into NS = 8 signed 7-bit slices, x = sum_p a_p 2^-(6+7p), a_p in [-64, 64]
-// (exact: each step removes the leading 7 bits of the remainder).  Then
+// (balanced base-128 digits of rint(x 2^55): exact up to 2^-56 of the row maximum).  Then
 //     T_ij = 2^(e_i + f_j - 12) * sum_t 2^(-7t) G_t,   G_t = sum_{p+q=t} (a_p c_q^T)_ij   (int32, exact: |G_t| < 2^25)
 // and only t = 0..7 is kept (36 int8 products): the dropped terms are below 2^-52 of (row max)(column max) K, i.e. of
 // the order of the rounding error bound of the FP64 product itself.  The eight G_t live in eight TMEM accumulators of
@@ -14,8 +17,11 @@
 // core-matrix order of the UMMA shared-memory descriptor (8 rows x 16 bytes per core matrix), grouped so that everything
 // one pipeline stage needs (32 bytes of K for all 8 slices of a 128-row block) is ONE contiguous range: the producer
 // thread moves it with cp.async.bulk (global -> shared, mbarrier completion), no tensor map needed.  Warp roles:
-// warp 0 producer, warp 1 MMA issuer (one thread, 36 MMAs per stage, tcgen05.commit releases the stage), warps 2-5
-// epilogue (tcgen05.ld, fp64 recombination, scaling, fused row dot, 64-byte row segments of T).
+// warp 0 producer, warp 1 MMA issuer (one elected lane, 36 MMAs per stage, tcgen05.commit releases the stage), warps 2-5
+// epilogue (tcgen05.ld, integer recombination of the eight accumulators, power-of-two scaling, fused row dot against a K
+// tile staged in shared memory while the MMAs run, 64-byte row segments of T).  The main loop runs at 50 cycles per
+// 128x64x32 MMA, the shared-memory operand bandwidth (6 KB per MMA at 128 B/clk); the epilogue cannot overlap the next
+// tile because the eight accumulators fill TMEM (11 % of the kernel).
 // Descriptor encodings: cute/arch/mma_sm100_desc.hpp of the vendored CUTLASS; verified by tools/probes/umma_i8_probe.cu.
 #include <cstdint>
 
@@ -27,15 +33,15 @@ constexpr int OZ_NS = 8;          // slices per operand
 constexpr int OZ_BM = 128;        // rows of K per tile (TMEM lanes)
 constexpr int OZ_BN = 64;         // columns per tile (TMEM columns per accumulator)
 constexpr int OZ_KS = 32;         // bytes of K per pipeline stage = one MMA k-step
-constexpr int OZ_STAGES = 2;         // row-quadratic kernel (leaves shared memory for a co-resident slicer CTA; 3 measured equal)
-constexpr int OZ_SYRK_STAGES = 4;    // SYRK kernel (no K tile to stage)
-constexpr int OZ_KLD = OZ_BN + 2;     // leading dimension (doubles) of the staged K tile: conflict-free 16-byte row reads
+constexpr int OZ_STAGES = 2;       // row-quadratic kernel: leaves shared memory for a co-resident slicer CTA (3 measured equal)
+constexpr int OZ_SYRK_STAGES = 4;  // SYRK kernel (no K tile to stage)
+constexpr int OZ_KLD = OZ_BN + 2;  // leading dimension (doubles) of the staged K tile: conflict-free 16-byte row reads
 constexpr int OZ_A_STAGE = OZ_NS * OZ_BM * OZ_KS;   // 32 KB
 constexpr int OZ_B_STAGE = OZ_NS * OZ_BN * OZ_KS;   // 16 KB
 constexpr int OZ_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------------------------------
-// slicing: one warp per row of X (R x Kd, fp64, row stride ldx); rows >= R are written as zeros.
+// slicing of X (R x Kd, fp64, row stride ldx); rows >= R are written as zeros.
 // out layout, BR = rows per block (128 for K, 64 for C):
 //   byte offset = ((((r / BR) * nks + k / 32) * 8 + p) * 2 + (k % 32) / 16) * (BR * 16) + ((r % BR) / 8) * 128 + (r % 8) * 16 + k % 16
 // expo[r]: x = X[r, :] * 2^-expo[r] in [-1, 1]
