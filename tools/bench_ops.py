@@ -104,6 +104,12 @@ def main():
         ms, best = timeit(lambda: ops.dgemm(A1, A2, C=Out))
         report("dgemm_MMM[%s]" % nm, ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
     check(lib().npgp_set_gemm_config(5), "cfg")
+    # the same two contractions on the int8 tensor cores (exact Ozaki split, csrc/ozaki.cu), slicing passes included
+    Cs = 0.5 * (Cm + Cm.T)
+    ms, best = timeit(lambda: ops.rowquad_i8(K, Cs, T=T))
+    report("rowquad_i8[tcgen05, slicing included]", ms, best, fp64_equiv_tflops=round(2 * B * M * M / best / 1e9, 2))
+    ms, best = timeit(lambda: ops.syrk_i8(K, out=Out))
+    report("syrk_i8[tcgen05, slicing included]", ms, best, fp64_equiv_tflops_useful=round(B * M * (M + 64) / best / 1e9, 2))
     ms, best = timeit(lambda: torch.matmul(A1, A2, out=Out))
     report("cublas_dgemm_MMM(reference point)", ms, best, tflops=round(2 * M ** 3 / best / 1e9, 2))
     ms, best = timeit(lambda: torch.matmul(K, Cm, out=T), iters=5)
