@@ -39,6 +39,9 @@ constexpr int OZ_KLD = OZ_BN + 2;  // leading dimension (doubles) of the staged 
 constexpr int OZ_A_STAGE = OZ_NS * OZ_BM * OZ_KS;   // 32 KB
 constexpr int OZ_B_STAGE = OZ_NS * OZ_BN * OZ_KS;   // 16 KB
 constexpr int OZ_THREADS = 192;
+#ifndef OZ_SLICE_MINB
+#define OZ_SLICE_MINB 2  // two 512-thread slicer CTAs per SM (64 registers, 132 bytes of spill): the pass is HBM/latency bound
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // slicing of X (R x Kd, fp64, row stride ldx); rows >= R are written as zeros.
@@ -84,7 +87,7 @@ __device__ __forceinline__ void oz_store_slices(const double (&v)[16], double sc
 // row maximum is reduced through shuffles + shared memory; the 8 lanes of a row group write 128 contiguous bytes (one
 // core matrix) per slice.
 template <int BR>
-__global__ void __launch_bounds__(512) oz_slice_kernel(int R, int Rpad, int Kd, const double* __restrict__ X, long ldx,
+__global__ void __launch_bounds__(512, OZ_SLICE_MINB) oz_slice_kernel(int R, int Rpad, int Kd, const double* __restrict__ X, long ldx,
                                                        int8_t* __restrict__ out, int* __restrict__ expo) {
   __shared__ double smax[16][8];
   __shared__ int sexp[8];
