@@ -75,3 +75,26 @@ def test_kmeans_inducing_points(gold):
     assert dataprep.kmeans_inducing_points(394, X).shape == (394, 2)
     with pytest.raises(ValueError):
         dataprep.kmeans_inducing_points(500, X)
+
+
+def test_experiment_drivers_defaults_and_data_without_gpu():
+    """The experiment drivers keep the reference scripts' option defaults (experiments/spatial_exp.py:54-81,
+    spatio_temporal_exp.py:143-145, deepgp_spatial_bench.py:34-37,66) and load the committed data tables; running them
+    needs a GPU and must say so."""
+    from experiments import deepgp_spatial_bench as dg, spatial_exp as se, spatio_temporal_exp as ste
+    a = se.parse_args([])
+    assert (a.n_iter, a.splits, a.lr, a.prior_scale, a.prior_ell, a.prior_mean, a.noise, a.scale, a.train_percent) == (
+        5000, 10, 1e-2, 1.0, 1.3, 0.3, 0.011, 0.644, 80.0)
+    x, y = se.load_khyber_data()
+    assert x.shape == (394, 2) and y.shape == (394,) and x.dtype == torch.float64
+    b = ste.parse_args([])
+    assert (b.n_iter, b.lr) == (500, 0.015)
+    xtr, ytr, xte, yte, meany, stdy = ste.load_train_test()
+    assert xtr.shape == (172, 3) and xte.shape == (43, 3) and ytr.shape == (172,)
+    c = dg.parse_args([])
+    assert (c.num_epochs, c.num_samples, c.num_layers, c.batch_size, c.states) == (400, 3, 4, 315, 10)
+    assert dg.load_table().shape == (394, 3)
+    if not torch.cuda.is_available():
+        for mod in (se, ste, dg):
+            with pytest.raises(RuntimeError, match="CUDA"):
+                mod.main([])
