@@ -104,56 +104,73 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(variant, rows, M, threads, repeats=2):
-    """Seconds for one ELBO forward + autograd backward of the oracle on `rows` minibatch rows (host cores)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def _inv_softplus(v: float) -> float:
+    return v + math.log(-math.expm1(-v))
+
+
+def oracle_step(variant, x, y, Z, kw, threads, repeats=2, chunk=2048):
+    """One -ELBO forward + autograd backward of the CPU oracle (oracle/gibbs_oracle.py, the restated reference path) on the
+    given rows with the bench's parameters.  Returns (best seconds, loss, gradients by parameter name).  Imports nothing
+    from the product package."""
     from oracle import gibbs_oracle as o
-    from nonstationary_precip_b200.svgp import _inv_softplus
     torch.set_num_threads(threads)
-    kw = make_params(variant, M, DIM)
-    g = torch.Generator().manual_seed(7)
-    x = torch.rand(rows, DIM, generator=g, dtype=torch.float64) * 2 - 1
-    y = torch.sin(3 * x[:, 0]) + 0.1 * torch.randn(rows, generator=g, dtype=torch.float64)
-    Z = torch.rand(M, DIM, generator=g, dtype=torch.float64) * 2 - 1
-    P = dict(Z=Z.clone(), m=kw["m"].clone(), Ls=kw["Ls"].clone(), ro=torch.tensor(_inv_softplus(kw["outputscale"])),
-             rn=torch.tensor(_inv_softplus(kw["noise"] - 1e-4)))
+    c = lambda t: t.detach().cpu().clone()
+    P = dict(Z=c(Z), m=c(kw["m"]), Ls=c(kw["Ls"]),
+             raw_outputscale=c(kw["raw_outputscale"]).reshape(()) if "raw_outputscale" in kw else
+             torch.tensor(_inv_softplus(kw["outputscale"]), dtype=torch.float64),
+             raw_noise=c(kw["raw_noise"]).reshape(()) if "raw_noise" in kw else
+             torch.tensor(_inv_softplus(kw["noise"] - 1e-4), dtype=torch.float64))
     if variant == "diag":
-        P["f"] = kw["log_ell_z"].clone()
-        extra = lambda: dict(log_ell_z=P["f"], prior_c=kw["prior_c"], prior_os=kw["prior_os"], prior_lam=kw["prior_lam"])
+        P["log_ell_z"] = c(kw["log_ell_z"])
+        extra = lambda: dict(log_ell_z=P["log_ell_z"], prior_c=c(kw["prior_c"]), prior_os=c(kw["prior_os"]),
+                             prior_lam=c(kw["prior_lam"]))
     else:
-        P["f"], P["D"] = kw["H"].clone(), kw["Dm"].clone()
-        extra = lambda: dict(H=P["f"], Dm=P["D"], row_os=torch.tensor(1.0, dtype=torch.float64), row_lam=kw["row_lam"])
+        P["H"], P["D"] = c(kw["H"]), c(kw["Dm"])
+        extra = lambda: dict(H=P["H"], Dm=P["D"], row_os=torch.tensor(float(kw["row_os"]), dtype=torch.float64),
+                             row_lam=c(kw["row_lam"]))
     for v in P.values():
         v.requires_grad_(True)
-    best = float("inf")
+    x, y = c(x), c(y)
+    best, loss = float("inf"), None
     for it in range(repeats + 1):
         for v in P.values():
             v.grad = None
         t0 = time.perf_counter()
-        loss = -o.svgp_gibbs_elbo(x, y, N_TOTAL, P["Z"], P["m"], P["Ls"], P["ro"], P["rn"], variant, chunk=2048,
-                                  **extra())
+        loss = -o.svgp_gibbs_elbo(x, y, N_TOTAL, P["Z"], P["m"], P["Ls"], P["raw_outputscale"], P["raw_noise"], variant,
+                                  chunk=chunk, **extra())
         loss.backward()
         dt = time.perf_counter() - t0
         if it > 0 or repeats == 0:
             best = min(best, dt)
-    return best
+    grads = {k: v.grad.detach().reshape(-1) if v.grad is not None else torch.zeros(v.numel(), dtype=torch.float64)
+             for k, v in P.items()}
+    grads["Ls"] = torch.tril(P["Ls"].grad.detach()).reshape(-1)
+    return best, float(loss.detach()), grads
+
+
+def headline_sample(variant, rows):
+    """The bench's own inputs: first `rows` rows of minibatch 0, the same inducing points and initial parameters."""
+    x_h, y_h, perm = make_data(N_TOTAL, DIM)
+    return x_h[:rows].contiguous(), y_h[:rows].contiguous(), x_h[perm[:M_IND]].contiguous(), make_params(variant, M_IND, DIM)
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     threads = os.cpu_count() or 1
     rows = args.ref_rows
+    x, y, Z, kw = headline_sample(args.variant, rows)
     times = []
     for i in range(args.warmup + args.steps):
-        t = cpu_reference_step_time(args.variant, rows, M_IND, threads, repeats=0 if i else 1)
+        t, _, _ = oracle_step(args.variant, x, y, Z, kw, threads, repeats=0)
         if i >= args.warmup:
             times.append(t)
     t_step = sum(times) / len(times) * (B_GLOBAL / rows)
     val = 1.0 / t_step
-    sample = "%d of %d minibatch rows per step (M=%d), time scaled x%d; fwd+autograd bwd, torch %s CPU fp64" % (
-        rows, B_GLOBAL, M_IND, B_GLOBAL // rows, torch.__version__)
+    sample = "first %d of the %d rows of minibatch 0 per step (same x, y, Z, parameters as the GPU arm; M=%d), time scaled " \
+             "x%d; fwd+autograd bwd, torch %s CPU fp64" % (rows, B_GLOBAL, M_IND, B_GLOBAL // rows, torch.__version__)
     line = {"impl": "reference", "metric": "SVGP-Gibbs ELBO steps/s", "value": val, "unit": "steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -340,20 +357,42 @@ def run_ours(args):
                                   "int8 entry); unit is int8 TOP/s"}
     kxz_gbs = 16.0 * Bl * M_IND / (sec["kxz_fwd"] + sec["kxz_bwd"]) / 1e6
 
+    # ---- parity at the headline size, in the same run: the GPU path and the CPU oracle on the SAME rows (the first
+    # ref_rows rows of minibatch 0), the same Z and the same parameters; the oracle pass is also the CPU baseline timing
+    parity = t_cpu = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        cpu_rows = args.ref_rows
+        model.restore(snap)
+        for k in range(3):  # a few optimiser steps first: at the initial S = I the quadratic term T = K C is identically 0
+            step_resident(k)
+        state = dict(kw, **{k: v.detach().clone() for k, v in model.p.items()})
+        state["Dm"] = state.get("D")
+        got_loss = float(model.loss_and_grad(X[:cpu_rows], Y[:cpu_rows], 1, cpu_rows))
+        info = int(model.last["info"])
+        got = {k: v.detach().reshape(-1).cpu().clone() for k, v in model.g.items()}
+        sec_cpu, want_loss, want = oracle_step(args.variant, x_h[:cpu_rows], y_h[:cpu_rows], state["Z"], state, threads)
+        t_cpu = sec_cpu * (B_GLOBAL / cpu_rows)
+        grel = {k: float((got[k] - want[k]).abs().max() / want[k].abs().max().clamp_min(1e-300)) for k in want}
+        parity = {"elbo_rel": abs(got_loss - want_loss) / abs(want_loss), "grad_rel_max": max(grel.values()),
+                  "grad_rel": grel, "rows": cpu_rows, "M": M_IND, "tol": 1e-6, "cholesky_info": info,
+                  "state": "parameters after 3 Adam steps from the bench's initial state",
+                  "against": "oracle/gibbs_oracle.py svgp_gibbs_elbo + autograd on the same x, y, Z and parameters"}
+        parity["ok"] = bool(parity["elbo_rel"] <= 1e-6 and parity["grad_rel_max"] <= 1e-6 and info == 0)
+
     if rank == 0:
         threads = os.cpu_count() or 1
         cpu_rows = args.ref_rows
-        t_cpu = cpu_reference_step_time(args.variant, cpu_rows, M_IND, threads) * (B_GLOBAL / cpu_rows) if world == 1 \
-            else None
         line = {
             "metric": "SVGP-Gibbs ELBO steps/s", "value": args.steps / (ms / 1e3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.gemm == "dmma" else "f64 (the two large GEMMs as exact int8 slice products, int32 accumulation)",
             "data": "synthetic",
-            "config": dict(workload_config(args), exec="cuda_graph + 3 streams" if args.exec == "graph" else "eager",
-                           gemm="FP64 DMMA" if args.gemm == "dmma" else
-                           "exact int8 Ozaki split on tcgen05 (FP64-equivalent results)"),
+            "config": workload_config(args),  # identical in both arms
+            "impl_detail": {"exec": "cuda_graph + 3 streams" if args.exec == "graph" else "eager",
+                            "gemm": "FP64 DMMA" if args.gemm == "dmma" else
+                            "exact int8 Ozaki split on tcgen05 (FP64-equivalent results)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},
@@ -374,14 +413,17 @@ def run_ours(args):
         if t_cpu is not None:
             line["cpu_baseline"] = {
                 "value": 1.0 / t_cpu, "unit": "steps/s", "cores": threads, "kind": "port",
-                "sample": "%d of %d minibatch rows (M=%d) fwd+autograd bwd of the oracle, time scaled x%d" % (
-                    cpu_rows, B_GLOBAL, M_IND, B_GLOBAL // cpu_rows)}
+                "sample": "first %d of the %d rows of minibatch 0 (same x, y, Z, parameters as the GPU arm; M=%d) fwd+autograd "
+                          "bwd of the oracle, time scaled x%d" % (cpu_rows, B_GLOBAL, M_IND, B_GLOBAL // cpu_rows)}
+            line["parity"] = parity
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)  # a fast step whose results differ from the reference's is not a result
 
 
 def main():
