@@ -45,6 +45,14 @@ class LogNormalPriorProcess(PositivePriorProcess):
                 batch_shape=torch.Size((input_dim,)), active_dims=active_dims)
         self.covar_module = covariance_function
 
+    def _active(self, x):
+        """gpytorch.Kernel.__call__ semantics of `self.covar_module(x)`: the (outer) kernel's active_dims select the
+        input columns once; with active_dims=(0,1) a 2-column input passes unchanged and a 3-column one keeps 0,1."""
+        ad = getattr(self.covar_module, "active_dims", None)
+        if ad is None:
+            return x
+        return x.index_select(-1, ad.to(x.device)).contiguous()
+
     def _hypers(self):
         D = self.input_dim
         lam = self.covar_module.base_kernel.lengthscale.reshape(D, -1)
@@ -54,6 +62,7 @@ class LogNormalPriorProcess(PositivePriorProcess):
 
     def _prior_cov(self, x):
         c, os, lam = self._hypers()
+        x = self._active(x)
         return torch.stack([F.rbf_ard(x, x, lam[b], os[b]) for b in range(self.input_dim)])
 
     def forward(self, x):
@@ -66,6 +75,7 @@ class LogNormalPriorProcess(PositivePriorProcess):
     def conditional_sample(self, x, given: Tuple[torch.Tensor, torch.Tensor], **kwargs):
         """exp(c + K(x, Xg) (K(Xg,Xg) + 1e-4 I)^-1 (log ell_g - c))  (reference :80-100) -> (D, n)."""
         xg, ell_g = given
+        x, xg = self._active(x), self._active(xg)
         c, os, lam = self._hypers()
         D, m = self.input_dim, xg.shape[0]
         eye = torch.eye(m, dtype=x.dtype, device=x.device)

@@ -41,8 +41,11 @@ class SparseSpatioTemporal_Nonstationary(ExactGP):
         z_sp = self.spatial_covar_module.base_kernel._z()
         prior_mean = self.spatial_covar_module.base_kernel.base_kernel.lengthscale_prior.mean_module(z_sp)
         self.register_parameter("log_ell_z", torch.nn.Parameter(prior_mean.detach().clone()))
+        # reference :52-55 hands the prior the FULL (M,3) inducing points; the prior's own active_dims=(0,1)
+        # (experiments/spatio_temporal_exp.py:111) then select columns 0,1 = (time, lon) for the log-prior term, while the
+        # field interpolation sees the (lon, lat) slice (gibbs_kernels.py:310-316).  Kept as the reference has it.
         self.register_prior("ell_z_prior", self.spatial_covar_module.base_kernel.base_kernel.lengthscale_prior,
-                            lambda module: (module.spatial_covar_module.base_kernel._z(), module.log_ell_z))
+                            lambda module: (module.spatial_covar_module.base_kernel.inducing_points, module.log_ell_z))
 
     def _covar(self, x):
         kt = self.temporal_covar_module(x)

@@ -252,14 +252,18 @@ class SGPRSpatioTemporalStream(torch.nn.Module):
         ell_z = torch.exp(self.log_ell_z)
         eye = torch.eye(M, dtype=torch.float64, device=self.Z.device)
         alphas, lp = [], self.Z.new_zeros(())
+        z_prior = self.Z[:, 0:2]  # the reference's prior term sees (time, lon): its closure passes the full (M,3) inducing
+        # points and the prior's active_dims=(0,1) pick columns 0,1 (spatio_temporal_models.py:52-55, spatio_temporal_exp.py:111)
         for b in range(D):
             Kp = F.rbf_ard(zs, zs, self.prior_lam[b], self.prior_os[b]) + 1e-4 * eye
             Lb, Pb = F.psd_safe_chol_inv(Kp)
             r = self.log_ell_z[b] - self.prior_c[b]
-            a = F.spd_solve(Pb, r)
-            alphas.append(a)
+            alphas.append(F.spd_solve(Pb, r))
             if self.include_prior:
-                lp = lp + (-0.5 * (r * a).sum() - torch.log(torch.diagonal(Lb)).sum() - 0.5 * M * LOG2PI) / M
+                Kq = F.rbf_ard(z_prior, z_prior, self.prior_lam[b], self.prior_os[b]) + 1e-4 * eye
+                Lq, Pq = F.psd_safe_chol_inv(Kq)
+                lp = lp + (-0.5 * (r * F.spd_solve(Pq, r)).sum() - torch.log(torch.diagonal(Lq)).sum()
+                           - 0.5 * M * LOG2PI) / M
         hyp = self.hyp_t()
         spatial = self._chol_ladder(F.gibbs_diag(zs, ell_z, zs, ell_z), "spatial Kzz")
         temporal = self._chol_ladder(ops.rbf_periodic(zt, zt, hyp), "temporal Kzz")

@@ -457,7 +457,10 @@ def st_sgpr_objective(x, y, Z, log_ell_z, hyp_t, os_s, noise, prior_c, prior_os,
     ll = -0.5 * (quad + logdet + n * LOG2PI)
     trace_t = -0.5 * (hyp_t[3] - (Rt * Rt).sum(-1)).sum() / noise
     trace_s = -0.5 * (1.0 - (Rs_u * Rs_u).sum(-1)).sum() / noise
-    lp = lognormal_prior_log_prob(Z[:, 1:3], log_ell_z, prior_c, prior_os, prior_lam).sum()
+    # the registered prior closure passes the FULL (M,3) inducing points (spatio_temporal_models.py:52-55) and the prior was
+    # built with active_dims=(0,1) (experiments/spatio_temporal_exp.py:111): Kernel.__call__ selects columns 0,1 = (time, lon)
+    # -- pinned by tests/golden/lognormal_prior_active_dims.npz, generated from the reference's own log_prob
+    lp = lognormal_prior_log_prob(Z[:, 0:2], log_ell_z, prior_c, prior_os, prior_lam).sum()
     return (ll + trace_t + trace_s + lp) / n
 
 

@@ -44,8 +44,13 @@ class Kernel(torch.nn.Module):
             object.__setattr__(self, name, prior)
 
     def __call__(self, x1, x2=None, diag=False, **params):
+        # gpytorch.kernels.Kernel.__call__: active_dims are applied HERE (index_select on the last dimension), once, by
+        # the outermost kernel that is called; ScaleKernel.forward then calls base_kernel.forward directly.
         if x2 is None:
             x2 = x1
+        if self.active_dims is not None:
+            idx = torch.as_tensor(self.active_dims, dtype=torch.long).reshape(-1)
+            x1, x2 = x1.index_select(-1, idx), x2.index_select(-1, idx)
         return _Lazy(self.forward(x1, x2, diag=diag, **params))
 
 

@@ -116,6 +116,55 @@ def multivariate_cases():
     torch.set_default_dtype(torch.float64)
 
 
+def multivariate_d3_case():
+    """The same forward lines (models/multivariate_gibbs_kernel.py:77-150) with d = 3, the dimension of BASELINE config 2.
+    Only the CONSTRUCTOR of the reference hard-codes d = 2 (:46,54,62); `forward` is dimension-generic, so the kernel
+    object is built without the constructor (`_bare`) and every arithmetic line runs verbatim.  |D_kk| >= 0.7 keeps the
+    3-D Sigma(h) positive definite."""
+    torch.set_default_dtype(torch.float64)
+    g = torch.Generator().manual_seed(177)
+    n1, n2, d = 28, 17, 3
+    x1 = torch.rand(n1, d, generator=g) * 2 - 1
+    x2 = torch.rand(n2, d, generator=g) * 2 - 1
+    H1 = torch.randn(n1, d, generator=g)
+    H2 = torch.randn(n2, d, generator=g)
+    Dm = torch.diag(torch.tensor([0.9, -1.1, 0.75]))
+    k = _bare(mgk.MultivariateGibbsKernel, H1, Dm, d)
+    k.expectation_conditional_matrix_variate_dist = lambda xs: H2
+    import contextlib
+    import io
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        K11 = k.forward(x1, x1)
+        K12 = k.forward(x1, x2)
+    npz("gibbs_full_d3_f64", x1=x1, x2=x2, H1=H1, H2=H2, Dm=Dm, K11=K11, K12=K12)
+
+
+def lognormal_active_dims_case():
+    """LogNormalPriorProcess(input_dim=2, active_dims=(0,1)) as experiments/spatio_temporal_exp.py:111 builds it, called
+    the two ways SparseSpatioTemporal_Nonstationary calls it: `log_prob` on the FULL (M,3) inducing points
+    (models/spatio_temporal_models.py:52-55: the prior's active_dims then select columns 0,1 = time, lon) and
+    `conditional_sample` on already-sliced (lon, lat) inputs (models/gibbs_kernels.py:310-316)."""
+    torch.set_default_dtype(torch.float64)
+    g = torch.Generator().manual_seed(178)
+    M, n, D = 14, 21, 2
+    prior = gk.LogNormalPriorProcess(input_dim=D, active_dims=(0, 1))
+    os_ = 0.5 + torch.rand(D, generator=g)
+    lam = 0.8 + torch.rand(D, 1, D, generator=g)
+    c = torch.log(torch.tensor(0.3)) + 0.1 * torch.randn(D, 1, generator=g)
+    prior.covar_module.outputscale = os_
+    prior.covar_module.base_kernel.lengthscale = lam
+    prior.mean_module.constant.data = c
+    Z3 = torch.randn(M, 3, generator=g)
+    x2 = torch.randn(n, 2, generator=g)
+    log_ell = torch.log(torch.tensor(0.3)) + 0.3 * torch.randn(D, M, generator=g)
+    with torch.no_grad():
+        logp_full = prior.log_prob((Z3, log_ell))
+        logp_lonlat = prior.log_prob((Z3[:, 1:3], log_ell))
+        ell_x = prior.conditional_sample(x2, given=(Z3[:, 1:3], torch.exp(log_ell)))
+    npz("lognormal_prior_active_dims", Z3=Z3, x2=x2, log_ell=log_ell, c=c.squeeze(-1), os=os_, lam=lam.squeeze(1),
+        log_prob_full_Z=logp_full, log_prob_lonlat=logp_lonlat, ell_x=ell_x)
+
+
 def sparse_multivariate_cases():
     """SparseMultivariateGibbsKernel: full constructor (:29-65), conditional mean of H (:67-80) and forward on inputs
     whose row count differs from M (:92-100, :113-123); default dtype float64."""
@@ -200,9 +249,9 @@ def spatio_temporal_data_case():
 
 
 if __name__ == "__main__":
-    gibbs_diag_cases()
-    lognormal_field_cases()
-    multivariate_cases()
-    sparse_multivariate_cases()
-    dataprep_and_metrics_cases()
-    spatio_temporal_data_case()
+    cases = [gibbs_diag_cases, lognormal_field_cases, multivariate_cases, multivariate_d3_case, lognormal_active_dims_case,
+             sparse_multivariate_cases, dataprep_and_metrics_cases, spatio_temporal_data_case]
+    want = sys.argv[1:]  # optional: names of the cases to (re)generate
+    for fn in cases:
+        if not want or fn.__name__ in want:
+            fn()

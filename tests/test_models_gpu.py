@@ -45,6 +45,22 @@ def test_lognormal_prior_process_golden(golden, tag):
         assert rel(K, g["K_cond"]) < 1e-10
 
 
+def test_lognormal_prior_active_dims_golden(golden):
+    """LogNormalPriorProcess(input_dim=2, active_dims=(0,1)) as the spatio-temporal experiment builds it: log_prob on the
+    full (M,3) inducing points uses columns (time, lon) like gpytorch.Kernel.__call__; fixture from the reference's lines."""
+    from nonstationary_precip_b200.models.gibbs_kernels import LogNormalPriorProcess
+    g = golden("lognormal_prior_active_dims")
+    prior = LogNormalPriorProcess(input_dim=2, active_dims=(0, 1)).cuda().double()
+    prior.covar_module.outputscale = g["os"].cuda()
+    prior.covar_module.base_kernel.lengthscale = g["lam"].cuda().unsqueeze(1)
+    prior.mean_module.constant.data = g["c"].cuda().unsqueeze(-1)
+    Z3, x2, log_ell = g["Z3"].cuda(), g["x2"].cuda(), g["log_ell"].cuda()
+    with torch.no_grad():
+        assert rel(prior.log_prob((Z3, log_ell)), g["log_prob_full_Z"]) < 1e-9
+        assert rel(prior.log_prob((Z3[:, 1:3].contiguous(), log_ell)), g["log_prob_lonlat"]) < 1e-9
+        assert rel(prior.conditional_sample(x2, given=(Z3[:, 1:3].contiguous(), torch.exp(log_ell))), g["ell_x"]) < 1e-10
+
+
 def test_exact_gp_map_objective_gradient_and_predict():
     """DiagonalExactGP + ExactMarginalLogLikelihood (config 1 shapes: n = 316, D = 2) vs the oracle."""
     from nonstationary_precip_b200.gp_base import ExactMarginalLogLikelihood, GaussianLikelihood

@@ -90,6 +90,15 @@ def test_gibbs_full_fwd_golden(ops, golden):
     assert rel(K, g32["K12"].double()) < 5e-6
 
 
+def test_gibbs_full_fwd_golden_d3(ops, golden):
+    """d = 3 fixture produced by the reference's own forward lines (tests/golden/make_golden.py multivariate_d3_case)."""
+    g = golden("gibbs_full_d3_f64")
+    x1, x2, Dm = dev(g["x1"], g["x2"], g["Dm"])
+    S1, S2 = ops.sigma_from_h_fwd(g["H1"].cuda(), Dm), ops.sigma_from_h_fwd(g["H2"].cuda(), Dm)
+    assert rel(ops.gibbs_full_fwd(x1, S1, x2, S2), g["K12"]) < 1e-12
+    assert rel(ops.gibbs_full_fwd(x1, S1, x1, S1), g["K11"]) < 1e-12
+
+
 @pytest.mark.parametrize("n1,n2,d", [(1, 3, 2), (45, 258, 2), (200, 515, 3), (513, 1024, 3)])
 def test_gibbs_full_fwd_bwd_random(ops, n1, n2, d):
     g = torch.Generator().manual_seed(n1 + n2)

@@ -42,6 +42,28 @@ def test_gibbs_full_vs_reference_lines(golden, tag, tol):
     assert rel(o.gibbs_full_K(g["x1"], g["x1"], S1, S1), g["K11"].double()) < tol
 
 
+def test_gibbs_full_d3_vs_reference_lines(golden):
+    """d = 3 (the dimension of BASELINE config 2): the reference's forward lines run with d = 3 (make_golden.py
+    multivariate_d3_case; only its constructor hard-codes 2)."""
+    g = golden("gibbs_full_d3_f64")
+    S1, S2 = o.sigma_from_H(g["H1"], g["Dm"]), o.sigma_from_H(g["H2"], g["Dm"])
+    assert rel(o.gibbs_full_K(g["x1"], g["x2"], S1, S2), g["K12"]) < 1e-13
+    assert rel(o.gibbs_full_K(g["x1"], g["x1"], S1, S1), g["K11"]) < 1e-13
+
+
+def test_lognormal_prior_active_dims_vs_reference_lines(golden):
+    """The spatio-temporal model's prior term: log_prob on the full (M,3) inducing points sees columns (0,1) = (time, lon);
+    the field interpolation sees the (lon, lat) slice."""
+    g = golden("lognormal_prior_active_dims")
+    lp_tl = o.lognormal_prior_log_prob(g["Z3"][:, 0:2], g["log_ell"], g["c"], g["os"], g["lam"])
+    assert rel(lp_tl, g["log_prob_full_Z"]) < 1e-11
+    lp_ll = o.lognormal_prior_log_prob(g["Z3"][:, 1:3], g["log_ell"], g["c"], g["os"], g["lam"])
+    assert rel(lp_ll, g["log_prob_lonlat"]) < 1e-11
+    assert rel(lp_ll, g["log_prob_full_Z"]) > 1e-2  # the two differ: the quirk is observable
+    ell_x = o.field_interp_diag(g["x2"], g["Z3"][:, 1:3], torch.exp(g["log_ell"]), g["c"], g["os"], g["lam"])
+    assert rel(ell_x, g["ell_x"]) < 1e-12
+
+
 def test_gibbs_full_mpmath_kv2():
     """KV2 inputs of SURVEY.md Appendix C evaluated with 50 digits.  (The 'all-fp64' numbers printed in the survey are
     themselves off by ~2e-9; the mpmath values below are the closed form of multivariate_gibbs_kernel.py:98-150.)"""
