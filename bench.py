@@ -26,6 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_TOTAL, M_IND, B_GLOBAL, DIM = 1 << 20, 1024, 65536, 3
+# dram__bytes_read.sum + dram__bytes_write.sum of one o8_rowquad_kernel launch at Bl = 65536 from the ncu --set full capture
+# summarised in profiles/ (None until that capture exists for the current kernel)
+TRAFFIC_ROWQUAD_BYTES = None
 
 
 def env_int(k, d):
@@ -329,32 +332,50 @@ def run_ours(args):
     rq_tf = 2.0 * Bl * M_IND * M_IND / sec["rowquad"] / 1e9
     i8_roof = None
     if args.gemm == "i8":
-        # dominant kernel of the int8 path: oz_rowquad_kernel alone (slices from the last step are still in the workspace)
+        # dominant kernel of the int8 path: o8_rowquad_kernel, timed alone on the digit planes the last step left in the
+        # model's buffers (real data), average of 5 launches with CUDA events on the launching stream
         from nonstationary_precip_b200 import ops as _ops
-        Kt = torch.rand(Bl, M_IND, dtype=torch.float64, device=dev)
-        Ct = torch.eye(M_IND, dtype=torch.float64, device=dev)
-        Tt, _ = _ops.rowquad_i8(Kt, Ct)
-        work = _ops._I8_WORK[(dev.index, Bl, M_IND)]
-        nbytes = lib().npgp_rowquad_i8_workspace_bytes(Bl, M_IND)
-        best = float("inf")
-        for _ in range(5):
+        wb = model._digit_buffers(Bl)
+        s_dev = torch.nn.functional.softplus(model.p["raw_outputscale"])
+        gvec = torch.randn(Bl, dtype=torch.float64, device=dev)
+        times = []
+        for it in range(7):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            check(lib().npgp_rowquad_i8_gemm_only(Bl, M_IND, ptr(Kt), Kt.stride(0), ptr(Tt), Tt.stride(0), None, ptr(work),
-                                                  nbytes, stream()), "gemm_only")
+            _ops.o8_rowquad_digits(Bl, M_IND, wb["Ad"], s_dev, wb["Cd"], wb["cexp"], wb["T"], q_part=wb["q_part"], gvec=gvec,
+                                   du_part=wb["du_part"])
             b.record()
             b.synchronize()
-            best = min(best, a.elapsed_time(b))
-        top = 36 * 2.0 * Bl * M_IND * M_IND / best / 1e9  # 36 int8 slice products per FP64-exact product
-        i8_peak = 2.0 * peaks.get("bf16_tflops", 2250.0)
-        i8_roof = {"bound": "tensor", "kernel": "oz_rowquad_kernel (T = K C as 36 exact int8 slice products, tcgen05 kind::i8 "
-                                                "+ TMEM)", "achieved": top, "peak": i8_peak, "unit": "TFLOP/s",
-                   "frac": top / i8_peak, "ms": best, "fp64_equivalent_tflops": 2.0 * Bl * M_IND * M_IND / best / 1e9,
-                   # dram__bytes_read.sum + dram__bytes_write.sum at Bl = 65536 (ncu, profiles/r01_ncu_oz_kernels.txt):
-                   # slices 537 MB + K tile 537 MB read, T 507 MB written
-                   "traffic": 1.591e9 if world == 1 else None,
-                   "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x dense bf16 on B200; no measured "
-                                  "int8 entry); unit is int8 TOP/s"}
+            if it >= 2:
+                times.append(a.elapsed_time(b))
+        rq_ms = sum(times) / len(times)
+        top = 28 * 2.0 * Bl * M_IND * M_IND / rq_ms / 1e9  # 28 int8 digit products per FP64-exact product
+
+        def i8_probe(n_tile, coll, reps=4096):
+            best = float("inf")
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                check(lib().npgp_i8_peak_probe(n_tile, coll, 148, reps, stream()), "i8 probe")
+                b.record()
+                b.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return 148.0 * reps * 8 * 2 * 128 * n_tile * 32 / best / 1e9  # TOP/s
+
+        i8_peak = i8_probe(256, 0)
+        i8_roof = {"bound": "tensor", "kernel": "o8_rowquad_kernel (T = K C as 28 exact int8 byte-digit products, tcgen05 "
+                                                "kind::i8 + TMEM; row dot and K^T g fused)", "achieved": top, "peak": i8_peak,
+                   "unit": "TFLOP/s", "frac": top / i8_peak, "ms": rq_ms,
+                   "fp64_equivalent_tflops": 2.0 * Bl * M_IND * M_IND / rq_ms / 1e9,
+                   # algorithmic bytes per launch: A digit planes read once (7 B/entry) + T written (8 B/entry) + C planes
+                   "algorithmic_bytes": (7.0 + 8.0) * Bl * M_IND + 7.0 * M_IND * M_IND,
+                   "traffic": TRAFFIC_ROWQUAD_BYTES if (world == 1 and TRAFFIC_ROWQUAD_BYTES) else None,
+                   "peak_source": "measured in this run: npgp_i8_peak_probe, back-to-back tcgen05.mma kind::i8 128x256x32 from "
+                                  "resident shared memory on 148 SMs (MEASURED_PEAKS.json has no int8 entry; 2 x its bf16 "
+                                  "burst figure would be %.0f); unit is int8 TOP/s" % (2.0 * peaks.get("bf16_tflops", 0.0)),
+                   "tile_shape_ceiling": {"what": "same probe at the engine's 128x64x32 tile shape (TMEM holds 7 accumulators "
+                                                  "of 64 columns): shared-memory operand feed bound",
+                                          "plain": i8_probe(64, 0), "collector_a_reuse": i8_probe(64, 1)}}
     kxz_gbs = 16.0 * Bl * M_IND / (sec["kxz_fwd"] + sec["kxz_bwd"]) / 1e6
 
     # ---- parity at the headline size, in the same run: the GPU path and the CPU oracle on the SAME rows (the first
@@ -387,12 +408,13 @@ def run_ours(args):
             "metric": "SVGP-Gibbs ELBO steps/s", "value": args.steps / (ms / 1e3), "unit": "steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64" if args.gemm == "dmma" else "f64 (the two large GEMMs as exact int8 slice products, int32 accumulation)",
+            "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(args),  # identical in both arms
             "impl_detail": {"exec": "cuda_graph + 3 streams" if args.exec == "graph" else "eager",
                             "gemm": "FP64 DMMA" if args.gemm == "dmma" else
-                            "exact int8 Ozaki split on tcgen05 (FP64-equivalent results)"},
+                            "FP64-exact int8 byte-digit products on tcgen05 (28 per product, int32 accumulation); "
+                                    "K(X,Z) stored as 7-byte digits only"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s",
                     "h2d_bytes_per_step": Bl * (DIM + 1) * 8 * world, "d2h_bytes_per_step": 8 * world},

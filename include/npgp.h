@@ -1,7 +1,9 @@
 /* npgp -- C ABI of the B200-native non-stationary (Gibbs) GP hot path.
  *
  * Every entry point takes raw DEVICE pointers (fp64, row-major), explicit sizes / leading dimensions and the CUDA
- * stream to run on; nothing allocates, nothing synchronises, nothing keeps global mutable state.  Return value:
+ * stream to run on; nothing allocates, nothing synchronises.  The only process-global state are three measurement /
+ * debugging switches (npgp_set_gemm_config, npgp_o8_set_collector, npgp_rowquad_i8_debug) and the diagnostic launch
+ * counter; none of them affects results.  Return value:
  * 0 = ok, < 0 = argument error (NPGP_E*), > 0 = a cudaError_t from the launch.  All calls are asynchronous.
  * Outputs documented as "accumulated" are added to with atomics and must be zeroed by the caller.
  *
@@ -152,36 +154,87 @@ int npgp_rbfper_fwd(int n1, int n2, const double* t1, const double* t2, const do
 int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const double* hyp, const double* G, long ldg,
                     double* out4, double* dt2, npgp_stream_t stream);
 
-/* Row-quadratic contraction on the integer tensor cores (tcgen05.mma kind::i8 + TMEM), exact Ozaki split of both
- * operands into 8 signed 7-bit slices (csrc/ozaki.cu): same contract as npgp_rowquad, C symmetric, M % 64 == 0, T 16-byte
- * aligned with even ldt.  work: npgp_rowquad_i8_workspace_bytes(n, M) bytes of device memory (slices + exponents).
- * Replaces the same reference lines as npgp_rowquad (k_ux1.matmul(...), models/gibbs_kernels.py:222-232; A^T (S - I) A of
- * the whitened SVGP). */
+/* ---- exact FP64 contractions on the integer tensor cores (csrc/oz8.cu, csrc/oz8.cuh) ----------------------------------
+ * Replaces the reference's dense n x M x M products: k_ux1.matmul(inv_root) and the Woodbury terms
+ * (models/gibbs_kernels.py:222-232), A^T (S - I) A of the whitened VariationalStrategy (models/dgps.py:25-35 through
+ * GPyTorch) and Phi = Kzx Kxz of the SGPR objective.  Every operand entry is the 56-bit integer rint(x 2^(55-e)) cut into
+ * its 7 bytes (top byte signed, the others unsigned), e a power-of-two exponent per row or per matrix; the 28 byte
+ * products with p + q <= 6 are accumulated exactly in int32 by tcgen05.mma kind::i8 and recombined in the epilogue.
+ * Results equal the FP64 product to its own rounding bound and are bit-exact on integer-valued data.
+ *
+ * General operands (contract of npgp_rowquad / npgp_wsyrk): C symmetric, M % 64 == 0 (SYRK: M % 128 == 0), M <= 4608,
+ * T 16-byte aligned with even ldt.  work: the *_workspace_bytes(n, M) bytes of device memory (digit planes, exponents,
+ * SYRK chunk partials).  The SYRK adds its row chunks in a fixed order: bitwise reproducible. */
 long npgp_rowquad_i8_workspace_bytes(int n, int M);
 int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk, double* T, long ldt, double* q, void* work,
-                              long work_bytes, npgp_stream_t stream); /* measurement helper: GEMM on the slices left in work */
+                              long work_bytes, npgp_stream_t stream); /* measurement helper: GEMM on the planes left in work */
 int npgp_rowquad_i8_slice_only(int n, int M, const double* K, long ldk, const double* C, long ldc, void* work,
                                long work_bytes, npgp_stream_t stream); /* slicing passes only; then ..._gemm_only */
-void npgp_rowquad_i8_debug(long long* dev_counters); /* optional: 8 cycle counters written by CTA 0 (NULL = off) */
+void npgp_rowquad_i8_debug(long long* dev_counters); /* debugging aid: 8 cycle counters written by CTA 0 (NULL = off) */
 int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt, double* q,
                     void* work, long work_bytes, npgp_stream_t stream);
-
-/* alpha * w0 * K^T K (symmetric M x M, M % 128 == 0) on the integer tensor cores: the equal-weights case of npgp_wsyrk
- * (w0 = *w0_dev, NULL: 1).  uniform_count / uniform_target (optional): device-side gate as in npgp_wsyrk_hint, the kernel
- * only runs when *uniform_count == uniform_target; accumulate != 0 adds to Out.  work: npgp_syrk_i8_workspace_bytes(n, M).
- * npgp_wsyrk_weighted_only is the complementary half: Out = alpha K^T diag(w) K when the weights are NOT all equal, else 0. */
+/* alpha * w0 * K^T K (symmetric M x M): the equal-weights case of npgp_wsyrk (w0 = *w0_dev, NULL: 1).  uniform_count /
+ * uniform_target (optional): device-side gate as in npgp_wsyrk_hint, the kernels only run when *uniform_count ==
+ * uniform_target; accumulate != 0 adds to Out.  npgp_wsyrk_weighted_only is the complementary half: Out = alpha K^T diag(w) K
+ * when the weights are NOT all equal, else untouched. */
 long npgp_syrk_i8_workspace_bytes(int n, int M);
 int npgp_syrk_i8(int n, int M, double alpha, const double* K, long ldk, const double* w0_dev, const double* uniform_count,
                  double uniform_target, int accumulate, int phase, double* Out, long ldo, void* work, long work_bytes,
-                 npgp_stream_t stream); /* phase: 0 slice + run, 1 slicing passes only, 2 run on the slices left in work */
+                 npgp_stream_t stream); /* phase: 0 slice + run, 1 slicing passes only, 2 run on the planes left in work */
 int npgp_syrk_i8_prepare(int n, int M, const double* K, long ldk, const double* w, double* wsum, void* work,
                          long work_bytes, npgp_stream_t stream); /* phase 1 + fused wsum[j] = sum_i w_i K_ij (w, wsum may be NULL) */
 int npgp_wsyrk_weighted_only(int n, int M, double alpha, const double* K, long ldk, const double* w,
                              const double* uniform_count, double uniform_target, double* Out, long ldo,
                              npgp_stream_t stream);
 
-/* ---- measurement helper: FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop), see csrc/peak.cu ---- */
+/* Digit-plane level (the SVGP step's path: K(X,Z) is never materialised in FP64).
+ * npgp_o8_digits_bytes: size of the planes of a rows x Kd matrix (block_rows 128: A operand, 64: symmetric B operand).
+ * npgp_o8_slice_rows:   planes + per-row exponents (ceil(R / block_rows) * block_rows ints) of an arbitrary FP64 matrix. */
+long npgp_o8_digits_bytes(int rows, int Kd, int block_rows);
+int npgp_o8_slice_rows(int R, int Kd, const double* X, long ldx, int block_rows, void* digits, int* expo,
+                       npgp_stream_t stream);
+/* Gibbs kernels emitted as digit planes: the same arithmetic as npgp_gibbs_diag_fwd / npgp_gibbs_full_fwd (same reference
+ * lines), 7 bytes per pair instead of 8, scale (device scalar, required) bounds the entries and fixes the matrix-wide
+ * exponent.  n2 % 32 == 0.  Optional fused K u: Ku_part (npgp_gibbs_digits_splits(n1, n2) x ku_stride) receives per-column-
+ * split partial sums (plain stores; add them in index order, e.g. npgp_mu_gmu_parts). */
+int npgp_gibbs_digits_splits(int n1, int n2);
+int npgp_gibbs_diag_fwd_digits(int D, int n1, int n2, const double* x1, const double* ell1, const double* x2,
+                               const double* ell2, const double* scale, void* digits, const double* u, double* Ku_part,
+                               long ku_stride, npgp_stream_t stream);
+int npgp_gibbs_full_fwd_digits(int d, int n1, int n2, const double* x1, const double* S1, const double* x2, const double* S2,
+                               double jitter, const double* scale, void* digits, const double* u, double* Ku_part,
+                               long ku_stride, npgp_stream_t stream);
+/* T = K C from planes.  a_expo NULL: matrix-wide exponent from *a_scale.  Kmat (optional): FP64 K for the row dot, else K is
+ * rebuilt from the planes.  q (optional): q_stride == 0 -> q[i] += rowdot (atomics); q_stride >= n -> q[cb * q_stride + i] =
+ * partial of column block cb (M / 64 blocks; deterministic).  gvec / du_part (optional): du_part[rb * M + j] = sum over the
+ * rows of row block rb (128 rows) of gvec_i K_ij -- K^T g_mu of the ELBO backward from the K tiles the kernel holds anyway. */
+int npgp_o8_rowquad_digits(int n, int M, const void* a_digits, const int* a_expo, const double* a_scale,
+                           const void* c_digits, const int* c_expo, const double* Kmat, long ldk, double* T, long ldt,
+                           double* q, long q_stride, const double* gvec, double* du_part, npgp_stream_t stream);
+int npgp_o8_sum_partials(int nb, int N, const double* part, double* out, npgp_stream_t stream); /* out[j] = sum_b part[b*N+j] */
+/* Out (+)= alpha * w0 * (K^T K - sum_{i in skip} k_i k_i^T) from the ROW-layout planes of K (n x M, matrix-wide scale
+ * *x_scale), read MN-major: no transposed copy.  skip_count / skip_rows (optional): rows of weight 0 (clamped variances).
+ * part: npgp_o8_syrk_part_bytes(n, M) bytes.  M % 128 == 0. */
+long npgp_o8_syrk_part_bytes(int n, int M);
+int npgp_o8_syrk_digits(int n, int M, const void* x_digits, const double* x_scale, double alpha, const double* w0_dev,
+                        const int* skip_count, const int* skip_rows, int accumulate, double* Out, long ldo, void* part,
+                        long part_bytes, npgp_stream_t stream);
+int npgp_o8_set_collector(int on); /* measurement switch: A-operand collector reuse hints (default 1) */
+
+/* Deterministic (two-stage, fixed order) variants of the ELBO reductions used with the digit-plane path. */
+int npgp_mu_gmu_parts(int n, const double* y, const double* mu_part, int nparts, long stride, const double* noise,
+                      double wscale, double* mu, double* gmu, npgp_stream_t stream);
+long npgp_gauss_ell_parts_workspace_bytes(int n);
+int npgp_gauss_ell_parts(int n, const double* y, const double* mu, const double* q_part, int nq, long q_stride,
+                         const double* kdiag, double jitter_xx, double min_var, const double* noise, double wscale,
+                         double* var_out, double* gmu, double* gv, double* acc4, int* skip_count, int* skip_rows, void* work,
+                         long work_bytes, npgp_stream_t stream);
+
+/* ---- measurement helpers (csrc/peak.cu): FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop) and the int8
+ * tensor-core ceiling (blocks x reps x 8 back-to-back tcgen05.mma kind::i8 of 128 x n_tile x 32 from resident shared
+ * memory; n_tile 256 = densest shape, 64 = the digit engine's tile; collector = A reuse hints) ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
+int npgp_i8_peak_probe(int n_tile, int collector, int blocks, int reps, npgp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -39,12 +39,26 @@ _SIGS = {
     "npgp_syrk_i8_prepare": ([_i, _i, _p, _l, _p, _p, _p, _l, _p], _i),
     "npgp_wsyrk_weighted_only": ([_i, _i, _d, _p, _l, _p, _p, _d, _p, _l, _p], _i),
     "npgp_rowquad_i8": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _p], _i),
+    "npgp_o8_set_collector": ([_i], _i),
+    "npgp_o8_digits_bytes": ([_i, _i, _i], _l),
+    "npgp_o8_slice_rows": ([_i, _i, _p, _l, _i, _p, _p, _p], _i),
+    "npgp_o8_rowquad_digits": ([_i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _l, _p, _p, _p], _i),
+    "npgp_o8_sum_partials": ([_i, _i, _p, _p, _p], _i),
+    "npgp_o8_syrk_part_bytes": ([_i, _i], _l),
+    "npgp_o8_syrk_digits": ([_i, _i, _p, _p, _d, _p, _p, _p, _i, _p, _l, _p, _l, _p], _i),
+    "npgp_gibbs_digits_splits": ([_i, _i], _i),
+    "npgp_gibbs_full_fwd_digits": ([_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p, _l, _p], _i),
+    "npgp_gibbs_diag_fwd_digits": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p], _i),
+    "npgp_mu_gmu_parts": ([_i, _p, _p, _i, _l, _p, _d, _p, _p, _p], _i),
+    "npgp_gauss_ell_parts_workspace_bytes": ([_i], _l),
+    "npgp_gauss_ell_parts": ([_i, _p, _p, _p, _i, _l, _p, _d, _d, _p, _d, _p, _p, _p, _p, _p, _p, _p, _l, _p], _i),
     "npgp_wsyrk": ([_i, _i, _d, _p, _l, _p, _p, _l, _p], _i),
     "npgp_wsyrk_hint": ([_i, _i, _d, _p, _l, _p, _p, _d, _p, _l, _p], _i),
     "npgp_symmetrize": ([_i, _p, _l, _i, _p], _i),
     "npgp_potrf_workspace_bytes": ([_i], _l),
     "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
+    "npgp_i8_peak_probe": ([_i, _i, _i, _i, _p], _i),
     "npgp_set_gemm_config": ([_i], _i),
     "npgp_colwsum": ([_i, _i, _p, _l, _p, _p, _p], _i),
     "npgp_gemv_n": ([_i, _i, _p, _l, _p, _p, _p], _i),
@@ -103,8 +117,8 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise NpgpError("npgp kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device.type)
-    if t.dtype not in (torch.float64, torch.int32):
-        raise NpgpError("npgp kernels are fp64 (got %s)" % t.dtype)
+    if t.dtype not in (torch.float64, torch.int32, torch.uint8, torch.int8):
+        raise NpgpError("npgp kernels take fp64 data (int32 exponents / indices, uint8 digit planes); got %s" % t.dtype)
     return t.data_ptr()
 
 

@@ -114,6 +114,71 @@ __global__ void adam_dev_kernel(long n, double* __restrict__ p, const double* __
 
 __global__ void bump_step_kernel(double* step_dev) { step_dev[0] += 1.0; }
 
+// ---- deterministic variants used with the digit-plane path (no FP64 atomics) -----------------------------------------
+// mu_i = sum_s mu_part[s * stride + i] (partials of the fused K u, added in index order);  gmu_i = wscale (y_i - mu_i)/noise
+__global__ void __launch_bounds__(256) mu_gmu_parts_kernel(int n, const double* __restrict__ y,
+                                                           const double* __restrict__ mu_part, int nparts, long stride,
+                                                           const double* __restrict__ noise_p, double wscale,
+                                                           double* __restrict__ mu, double* __restrict__ gmu) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double m = 0.0;
+  for (int s = 0; s < nparts; ++s) m += mu_part[(long)s * stride + i];
+  mu[i] = m;
+  gmu[i] = wscale * (y[i] - m) / *noise_p;
+}
+
+// As gauss_ell_kernel with q_i = sum_c q_part[c * q_stride + i]; per-block sums go to blk[3][gridDim.x] (plain stores) and
+// gauss_ell_finish_kernel adds them in block order.  Clamped rows are appended to skip_rows (their weight in K^T W K is 0).
+__global__ void __launch_bounds__(256) gauss_ell_parts_kernel(int n, const double* __restrict__ y, const double* __restrict__ mu,
+                                                              const double* __restrict__ q_part, int nq, long q_stride,
+                                                              const double* __restrict__ kdiag_p, double jitter_xx,
+                                                              double min_var, const double* __restrict__ noise_p,
+                                                              double wscale, double* __restrict__ var_out,
+                                                              double* __restrict__ gmu, double* __restrict__ gv,
+                                                              double* __restrict__ blk, int* __restrict__ skip_count,
+                                                              int* __restrict__ skip_rows) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const double s2 = *noise_p, kd = *kdiag_p;
+  double e = 0.0, r2v = 0.0, cnt = 0.0;
+  if (i < n) {
+    double qi = 0.0;
+    for (int c = 0; c < nq; ++c) qi += q_part[(long)c * q_stride + i];
+    double v = kd + jitter_xx + qi;
+    const bool clamped = v < min_var;
+    if (clamped) v = min_var;
+    const double r = y[i] - mu[i];
+    e = -0.5 * ((r * r + v) / s2 + log(s2) + 1.8378770664093453);
+    r2v = r * r + v;
+    cnt = clamped ? 0.0 : 1.0;
+    if (var_out) var_out[i] = v;
+    gmu[i] = wscale * r / s2;
+    gv[i] = clamped ? 0.0 : -0.5 * wscale / s2;
+    if (clamped && skip_count) skip_rows[atomicAdd(skip_count, 1)] = i;
+  }
+  double t = block_sum(e, red);
+  if (threadIdx.x == 0) blk[blockIdx.x] = t;
+  t = block_sum(r2v, red);
+  if (threadIdx.x == 0) blk[gridDim.x + blockIdx.x] = t;
+  t = block_sum(cnt, red);
+  if (threadIdx.x == 0) blk[2 * gridDim.x + blockIdx.x] = t;
+}
+
+// acc4 = [sum ell, sum ((y-mu)^2 + v), #unclamped rows, w0 = -0.5 wscale / noise (the weight of every unclamped row)]
+__global__ void __launch_bounds__(256) gauss_ell_finish_kernel(int nblk, const double* __restrict__ blk,
+                                                               const double* __restrict__ noise_p, double wscale,
+                                                               double* __restrict__ acc4) {
+  __shared__ double red[32];
+  for (int k = 0; k < 3; ++k) {
+    double a = 0.0;
+    for (int b = threadIdx.x; b < nblk; b += 256) a += blk[(long)k * nblk + b];  // fixed assignment, fixed tree
+    const double t = block_sum(a, red);
+    if (threadIdx.x == 0) acc4[k] = t;
+  }
+  if (threadIdx.x == 0) acc4[3] = -0.5 * wscale / *noise_p;
+}
+
 }  // namespace npgp
 
 using namespace npgp;
@@ -164,6 +229,43 @@ extern "C" int npgp_gauss_ell(int n, const double* y, const double* mu, const do
   if (!y || !mu || !q || !kdiag || !noise || !gmu || !gv || !acc3) return NPGP_EINVAL;
   gauss_ell_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n, y, mu, q, kdiag, jitter_xx, min_var, noise, wscale, var_out,
                                                          gmu, gv, acc3);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+
+// mu = sum of `nparts` partial mean vectors (stride apart, index order) and gmu = wscale (y - mu) / *noise: the first
+// gradient seed of the ELBO, available before the predictive variance is.
+extern "C" int npgp_mu_gmu_parts(int n, const double* y, const double* mu_part, int nparts, long stride, const double* noise,
+                                 double wscale, double* mu, double* gmu, cudaStream_t stream) {
+  if (n < 0 || nparts < 1 || stride < n) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!y || !mu_part || !noise || !mu || !gmu) return NPGP_EINVAL;
+  mu_gmu_parts_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(n, y, mu_part, nparts, stride, noise, wscale, mu, gmu);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+extern "C" long npgp_gauss_ell_parts_workspace_bytes(int n) { return 3L * ceil_div(n > 0 ? n : 1, 256) * (long)sizeof(double); }
+
+// npgp_gauss_ell with the quadratic term given as `nq` partial vectors (q_i = sum_c q_part[c * q_stride + i], index order)
+// and all reductions two-stage (bitwise reproducible).  acc4 (overwritten) = [sum ell, sum ((y-mu)^2 + v), #unclamped rows,
+// w0 = -0.5 wscale / noise].  skip_count / skip_rows (optional; *skip_count zeroed by the caller): indices of clamped rows.
+extern "C" int npgp_gauss_ell_parts(int n, const double* y, const double* mu, const double* q_part, int nq, long q_stride,
+                                    const double* kdiag, double jitter_xx, double min_var, const double* noise, double wscale,
+                                    double* var_out, double* gmu, double* gv, double* acc4, int* skip_count, int* skip_rows,
+                                    void* work, long work_bytes, cudaStream_t stream) {
+  if (n < 0 || nq < 0 || (nq > 0 && q_stride < n) || ((skip_count != nullptr) != (skip_rows != nullptr))) return NPGP_EINVAL;
+  if (!acc4 || !noise) return NPGP_EINVAL;
+  if (n > 0 && (!y || !mu || (nq > 0 && !q_part) || !kdiag || !gmu || !gv || !work)) return NPGP_EINVAL;
+  if (n > 0 && work_bytes < npgp_gauss_ell_parts_workspace_bytes(n)) return NPGP_EWORKSPACE;
+  const int nblk = ceil_div(n, 256);
+  if (n > 0) {
+    gauss_ell_parts_kernel<<<nblk, 256, 0, stream>>>(n, y, mu, q_part, nq, q_stride, kdiag, jitter_xx, min_var, noise, wscale,
+                                                     var_out, gmu, gv, (double*)work, skip_count, skip_rows);
+    NPGP_LAUNCH_CHECK();
+  }
+  gauss_ell_finish_kernel<<<1, 256, 0, stream>>>(nblk, (const double*)work, noise, wscale, acc4);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

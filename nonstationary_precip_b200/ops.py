@@ -164,29 +164,53 @@ def rowquad(K, Cm, need_q=True, T=None):
     return T, q
 
 
-_I8_WORK = {}  # slice workspaces of the int8 GEMMs, keyed by shape; a handful of shapes recur (minibatch, last chunk)
-_I8_WORK_MAX = 6
+# ----------------------------------------------------------------------------------------------------------------------
+# exact int8 tensor-core contractions (csrc/oz8.cu).  Workspaces are owned by the CALLER (an I8Workspace per model / call
+# site): nothing here is process-global, so two models or two streams never share scratch memory.
+# ----------------------------------------------------------------------------------------------------------------------
+class I8Workspace:
+    """Scratch memory of the int8 contractions for one call site, keyed by shape.  Buffers are created on first use (do that
+    before CUDA-graph capture) and live as long as this object, so a captured graph that holds raw pointers into them
+    stays valid for the life of the model that owns the workspace."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device, dtype=torch.uint8):
+        buf = self._bufs.get(key)
+        item = torch.empty((), dtype=dtype).element_size()
+        if buf is None or buf.numel() * item < nbytes or buf.device != device:
+            buf = self._bufs[key] = torch.empty((nbytes + item - 1) // item, dtype=dtype, device=device)
+        return buf
 
 
-def _i8_work(key, nbytes, device):
-    work = _I8_WORK.get(key)
-    if work is None:
-        while len(_I8_WORK) >= _I8_WORK_MAX:  # drop the oldest entry (dict preserves insertion order)
-            _I8_WORK.pop(next(iter(_I8_WORK)))
-        work = _I8_WORK[key] = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=device)  # raw bytes
-    return work
+_DEFAULT_I8_WS = {}  # one workspace per (device, stream) for callers that do not pass their own
 
 
-def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
-    """rowquad on the integer tensor cores (tcgen05 kind::i8, exact Ozaki split, see csrc/ozaki.cu).  Cm must be
-    symmetric and M a multiple of 64.  The slice workspace is cached per (device, n, M).  `between`: callable run after
-    the slicing passes have been enqueued and before the tensor-core kernel."""
+def _ws(workspace, device):
+    if workspace is not None:
+        return workspace
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    if key not in _DEFAULT_I8_WS:
+        _DEFAULT_I8_WS[key] = I8Workspace()
+    return _DEFAULT_I8_WS[key]
+
+
+def set_i8_collector(on: bool):
+    """Measurement switch: A-operand collector-reuse hints of the digit products (default on)."""
+    check(lib().npgp_o8_set_collector(int(bool(on))), "npgp_o8_set_collector")
+
+
+def rowquad_i8(K, Cm, need_q=True, T=None, between=None, workspace=None):
+    """rowquad on the integer tensor cores (tcgen05 kind::i8, exact byte-digit split, see csrc/oz8.cu).  Cm must be
+    symmetric and M a multiple of 64.  `between`: callable run after the slicing passes have been enqueued and before the
+    tensor-core kernel."""
     n, M = K.shape
     if T is None:
         T = torch.empty(n, M, dtype=torch.float64, device=K.device)
     q = torch.zeros(n, dtype=torch.float64, device=K.device) if need_q else None
     nbytes = lib().npgp_rowquad_i8_workspace_bytes(n, M)
-    work = _i8_work((K.device.index, n, M), nbytes, K.device)
+    work = _ws(workspace, K.device).get(("rowquad", n, M), nbytes, K.device)
     if between is None:
         check(lib().npgp_rowquad_i8(n, M, ptr(K), K.stride(0), ptr(Cm), Cm.stride(0), ptr(T), T.stride(0), ptr(q),
                                     ptr(work), nbytes, stream()), "npgp_rowquad_i8")
@@ -199,40 +223,38 @@ def rowquad_i8(K, Cm, need_q=True, T=None, between=None):
     return T, q
 
 
-def _syrk_i8_work(K):
+def _syrk_i8_work(K, workspace):
     n, M = K.shape
     nbytes = lib().npgp_syrk_i8_workspace_bytes(n, M)
-    return _i8_work(("syrk", K.device.index, n, M), nbytes, K.device), nbytes
+    return _ws(workspace, K.device).get(("syrk", n, M), nbytes, K.device), nbytes
 
 
-def syrk_i8(K, w0=None, alpha=1.0, out=None):
-    """alpha * w0 * K^T K (symmetric M x M) on the integer tensor cores (exact Ozaki split, csrc/ozaki.cu); w0: device
-    scalar (or None); M must be a multiple of 128."""
+def syrk_i8(K, w0=None, alpha=1.0, out=None, workspace=None):
+    """alpha * w0 * K^T K (symmetric M x M) on the integer tensor cores (exact byte-digit split, csrc/oz8.cu); w0: device
+    scalar (or None); M must be a multiple of 128.  Bitwise reproducible (chunk partials are added in a fixed order)."""
     n, M = K.shape
     if out is None:
         out = torch.empty(M, M, dtype=torch.float64, device=K.device)
-    work, nbytes = _syrk_i8_work(K)
+    work, nbytes = _syrk_i8_work(K, workspace)
     check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w0), None, 0.0, 0, 0, ptr(out), out.stride(0),
                              ptr(work), nbytes, stream()), "npgp_syrk_i8")
     return out
 
 
-def syrk_i8_prepare(K, w=None):
-    """Slicing passes of the int8 SYRK only (column maxima, exponents, transposed slices into the cached workspace): HBM
-    bound, meant to run on a side stream under a tensor-bound kernel.  Follow with wsyrk_i8(..., prepared=True).  With
-    `w` (n,) the column-maximum pass also returns K^T w (M,), saving a separate pass over K."""
+def syrk_i8_prepare(K, w=None, workspace=None):
+    """Slicing passes of the int8 SYRK only (column maxima, exponents, transposed digit planes into the workspace).  Follow
+    with wsyrk_i8(..., prepared=True) on the same workspace.  With `w` (n,) the column-maximum pass also returns K^T w."""
     n, M = K.shape
-    work, nbytes = _syrk_i8_work(K)
+    work, nbytes = _syrk_i8_work(K, workspace)
     wsum = torch.empty(M, dtype=torch.float64, device=K.device) if w is not None else None
     check(lib().npgp_syrk_i8_prepare(n, M, ptr(K), K.stride(0), ptr(_c(w)), ptr(wsum), ptr(work), nbytes, stream()),
           "npgp_syrk_i8_prepare")
     return wsum
 
 
-def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None, prepared=False):
-    """alpha * K^T diag(w) K with the device-side equal-weights gate of `wsyrk`: equal weights (the normal case of the
-    SVGP step) run on the integer tensor cores, unequal ones on the FP64 weighted kernel; both are enqueued and the one
-    the flag does not select exits at once."""
+def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None, prepared=False, workspace=None):
+    """alpha * K^T diag(w) K with the device-side equal-weights gate of `wsyrk`: equal weights run on the integer tensor
+    cores, unequal ones on the FP64 weighted kernel; both are enqueued and the one the flag does not select exits at once."""
     n, M = K.shape
     if out is None:
         out = torch.empty(M, M, dtype=torch.float64, device=K.device)
@@ -240,10 +262,114 @@ def wsyrk_i8(K, w, uniform_count, uniform_target, alpha=1.0, out=None, prepared=
     check(lib().npgp_wsyrk_weighted_only(n, M, float(alpha), ptr(K), K.stride(0), ptr(w), ptr(uniform_count),
                                          float(uniform_target), ptr(out), out.stride(0), stream()),
           "npgp_wsyrk_weighted_only")
-    work, nbytes = _syrk_i8_work(K)
+    work, nbytes = _syrk_i8_work(K, workspace)
     check(lib().npgp_syrk_i8(n, M, float(alpha), ptr(K), K.stride(0), ptr(w), ptr(uniform_count), float(uniform_target), 1,
                              2 if prepared else 0, ptr(out), out.stride(0), ptr(work), nbytes, stream()), "npgp_syrk_i8")
     return out
+
+
+# ---- digit-plane path: K(X,Z) exists only as 7 bytes per entry -------------------------------------------------------
+def digits_bytes(rows, Kd, block_rows=128):
+    return lib().npgp_o8_digits_bytes(rows, Kd, block_rows)
+
+
+def gibbs_digits_splits(n1, n2):
+    return lib().npgp_gibbs_digits_splits(n1, n2)
+
+
+def gibbs_diag_fwd_digits(x1, ell1, x2, ell2, scale, digits, u=None, Ku_part=None):
+    """Digit planes of scale * GibbsKernel(x1, x2) (row layout, see csrc/oz8.cuh) into `digits` (uint8); with u the partial
+    sums of K u go to Ku_part (splits, n1)."""
+    x1, ell1, x2, ell2, scale, u = map(_c, (x1, ell1, x2, ell2, scale, u))
+    n1, D = x1.shape
+    n2 = x2.shape[0]
+    check(lib().npgp_gibbs_diag_fwd_digits(D, n1, n2, ptr(x1), ptr(ell1), ptr(x2), ptr(ell2), ptr(scale), ptr(digits), ptr(u),
+                                           ptr(Ku_part), Ku_part.stride(0) if Ku_part is not None else 0, stream()),
+          "npgp_gibbs_diag_fwd_digits")
+    return digits
+
+
+def gibbs_full_fwd_digits(x1, S1p, x2, S2p, jitter, scale, digits, u=None, Ku_part=None):
+    x1, S1p, x2, S2p, scale, u = map(_c, (x1, S1p, x2, S2p, scale, u))
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    check(lib().npgp_gibbs_full_fwd_digits(d, n1, n2, ptr(x1), ptr(S1p), ptr(x2), ptr(S2p), float(jitter), ptr(scale),
+                                           ptr(digits), ptr(u), ptr(Ku_part),
+                                           Ku_part.stride(0) if Ku_part is not None else 0, stream()),
+          "npgp_gibbs_full_fwd_digits")
+    return digits
+
+
+def o8_slice_rows(X, block_rows, digits, expo):
+    """Digit planes + per-row exponents of an arbitrary FP64 matrix (block_rows 128: A operand, 64: symmetric B operand)."""
+    R, Kd = X.shape
+    check(lib().npgp_o8_slice_rows(R, Kd, ptr(X), X.stride(0), block_rows, ptr(digits), ptr(expo), stream()),
+          "npgp_o8_slice_rows")
+
+
+def o8_rowquad_digits(n, M, a_digits, a_scale, c_digits, c_expo, T, q_part=None, gvec=None, du_part=None, a_expo=None,
+                      Kmat=None):
+    """T = K C from digit planes; q_part (M/64, n) receives the per-column-block partials of rowdot(T, K); du_part
+    (ceil(n/128), M) the per-row-block partials of K^T gvec.  a_scale: device scalar bounding the entries of K (matrix-wide
+    exponent) unless per-row exponents a_expo are given."""
+    check(lib().npgp_o8_rowquad_digits(n, M, ptr(a_digits), ptr(a_expo), ptr(a_scale), ptr(c_digits), ptr(c_expo), ptr(Kmat),
+                                       Kmat.stride(0) if Kmat is not None else 0, ptr(T), T.stride(0), ptr(q_part),
+                                       q_part.stride(0) if q_part is not None else 0, ptr(gvec), ptr(du_part), stream()),
+          "npgp_o8_rowquad_digits")
+    return T
+
+
+def o8_sum_partials(part, out=None):
+    nb, N = part.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float64, device=part.device)
+    check(lib().npgp_o8_sum_partials(nb, N, ptr(part), ptr(out), stream()), "npgp_o8_sum_partials")
+    return out
+
+
+def o8_syrk_part_bytes(n, M):
+    return lib().npgp_o8_syrk_part_bytes(n, M)
+
+
+def o8_syrk_digits(n, M, digits, scale, part, w0=None, alpha=1.0, skip_count=None, skip_rows=None, out=None,
+                   accumulate=False):
+    """alpha * w0 * (K^T K - sum_{i in skip} k_i k_i^T) from the row-layout digit planes of K (read MN-major)."""
+    if out is None:
+        out = torch.empty(M, M, dtype=torch.float64, device=digits.device)
+    nbytes = part.numel() * part.element_size()
+    check(lib().npgp_o8_syrk_digits(n, M, ptr(digits), ptr(scale), float(alpha), ptr(w0), ptr(skip_count), ptr(skip_rows),
+                                    int(accumulate), ptr(out), out.stride(0), ptr(part), nbytes, stream()),
+          "npgp_o8_syrk_digits")
+    return out
+
+
+def mu_gmu_parts(y, mu_part, noise, wscale):
+    """mu = sum of the partial mean vectors (rows of mu_part), gmu = wscale (y - mu) / noise."""
+    nparts, n = mu_part.shape
+    mu = torch.empty(n, dtype=torch.float64, device=y.device)
+    gmu = torch.empty_like(mu)
+    check(lib().npgp_mu_gmu_parts(n, ptr(_c(y)), ptr(mu_part), nparts, mu_part.stride(0), ptr(noise), float(wscale), ptr(mu),
+                                  ptr(gmu), stream()), "npgp_mu_gmu_parts")
+    return mu, gmu
+
+
+def gauss_ell_parts(y, mu, q_part, kdiag, noise, jitter_xx=1e-4, min_var=1e-6, wscale=1.0, want_var=False,
+                    skip_count=None, skip_rows=None):
+    """Deterministic gauss_ell with q = sum of the rows of q_part.  Returns (acc4, gmu, gv, var); acc4[3] is the weight
+    w0 = -0.5 wscale / noise of every unclamped row; clamped rows are appended to skip_rows."""
+    n = y.shape[0]
+    z = lambda *s: torch.empty(*s, dtype=torch.float64, device=y.device)
+    gmu, gv = z(n), z(n)
+    var = z(n) if want_var else None
+    acc = z(4)
+    nbytes = lib().npgp_gauss_ell_parts_workspace_bytes(n)
+    work = z(nbytes // 8 + 1)
+    nq = q_part.shape[0] if q_part is not None else 0
+    check(lib().npgp_gauss_ell_parts(n, ptr(_c(y)), ptr(mu), ptr(q_part), nq, q_part.stride(0) if nq else 0, ptr(kdiag),
+                                     float(jitter_xx), float(min_var), ptr(noise), float(wscale), ptr(var), ptr(gmu), ptr(gv),
+                                     ptr(acc), ptr(skip_count), ptr(skip_rows), ptr(work), nbytes, stream()),
+          "npgp_gauss_ell_parts")
+    return acc, gmu, gv, var
 
 
 def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0):

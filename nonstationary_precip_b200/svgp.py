@@ -118,7 +118,8 @@ class SVGPGibbs:
         self.overlap = True
         # row-quadratic GEMM T = K C: "dmma" (FP64 tensor pipe, dgemm.cu) or "i8" (exact Ozaki split on tcgen05 int8,
         # ozaki.cu; needs M % 64 == 0).  Same result to FP64 rounding (tests/test_ozaki_gpu.py).
-        self.rowquad_impl = "i8"  # falls back to "dmma" per call when M is not a multiple of 64 (SYRK: 128)
+        self.rowquad_impl = "i8"  # falls back to "dmma" per call when M is not a multiple of 128
+        self._i8_bufs = {}  # digit planes / partial buffers of the int8 path, per local batch size (owned by this model)
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
 
@@ -180,9 +181,36 @@ class SVGPGibbs:
         return self.o.sigma_from_h_fwd(self.p["H"], self.p["D"])
 
     def _rowquad(self, K, C, T=None):
-        if self.rowquad_impl == "i8" and self.M % 64 == 0 and hasattr(self.o, "rowquad_i8"):
-            return self.o.rowquad_i8(K, C, T=T)
         return self.o.rowquad(K, C, T=T)
+
+    # ---- int8 tensor-core path: K(X_B, Z) exists only as byte-digit planes (csrc/gibbs_digits.cu, csrc/oz8.cu) -------
+    def _digits_mode(self):
+        return self.rowquad_impl == "i8" and self.M % 128 == 0 and hasattr(self.o, "o8_rowquad_digits")
+
+    def _digit_buffers(self, n):
+        """Persistent scratch for a local batch of n rows: digit planes of K and C, the T matrix, the deterministic partial
+        buffers.  Created on first use (before graph capture: capture() warms the step up first)."""
+        w = self._i8_bufs.get(n)
+        if w is None:
+            o, M, dev = self.o, self.M, self.dev
+            f64 = dict(dtype=torch.float64, device=dev)
+            u8 = dict(dtype=torch.uint8, device=dev)
+            nsplit = o.gibbs_digits_splits(n, M)
+            w = self._i8_bufs[n] = dict(
+                Ad=torch.empty(o.digits_bytes(n, M, 128), **u8), Cd=torch.empty(o.digits_bytes(M, M, 64), **u8),
+                cexp=torch.empty(M, dtype=torch.int32, device=dev), T=torch.empty(n, M, **f64),
+                mu_part=torch.empty(nsplit, n, **f64), q_part=torch.empty(M // 64, n, **f64),
+                du_part=torch.empty((n + 127) // 128, M, **f64),
+                syrk_part=torch.empty(max(1, o.o8_syrk_part_bytes(n, M) // 8), **f64),
+                skip_count=torch.zeros(1, dtype=torch.int32, device=dev),
+                skip_rows=torch.empty(n, dtype=torch.int32, device=dev))
+        return w
+
+    def _kernel_fwd_digits(self, x1, f1, x2, f2, scale, u, w):
+        if self.variant == "diag":
+            self.o.gibbs_diag_fwd_digits(x1, f1, x2, f2, scale, w["Ad"], u=u, Ku_part=w["mu_part"])
+        else:
+            self.o.gibbs_full_fwd_digits(x1, f1, x2, f2, self.kernel_jitter, scale, w["Ad"], u=u, Ku_part=w["mu_part"])
 
     def _fork(self):
         """Run the enclosed launches on the side stream, ordered after everything enqueued so far."""
@@ -288,26 +316,30 @@ class SVGPGibbs:
         P, u, E, C, Ls = zz["P"], zz["u"], zz["E"], zz["C"], zz["Ls"]
 
         # ---- data pass: K(X_B, Z) (+ mean), variance quadratic form, expected log-lik
-        with self._sec("kxz_fwd"):
-            K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
-        # the slicing passes of the int8 SYRK need only K: HBM bound, put on the second side stream exactly under the
-        # tensor-bound row-quadratic kernel (which leaves room for their CTAs on every SM)
-        i8_syrk = self.rowquad_impl == "i8" and M % 128 == 0 and hasattr(o, "wsyrk_i8")
-
-        du_box = []
-
-        def fork_syrk_slices():
-            # d(ELL)/d(mu) does not depend on the variance, so K^T g_mu rides on the column-maximum pass of the slicing
-            gmu_early = ((1.0 / Bg) * (yb - mu)) / noise
-            with self._fork2():
-                du_box.append(o.syrk_i8_prepare(K, gmu_early))
-
-        with self._sec("rowquad"):
-            if i8_syrk:
-                T, q = o.rowquad_i8(K, C, between=fork_syrk_slices)
-            else:
+        digits = self._digits_mode()
+        K = q = None
+        if digits:
+            # K is written once as 7-byte digits and consumed by both tensor-core contractions; every reduction of this
+            # branch is two-stage with a fixed order (no FP64 atomics)
+            w = self._digit_buffers(Bl)
+            with self._sec("kxz_fwd"):
+                self._kernel_fwd_digits(xb, fx, Z, fz, s, u, w)
+                # d(ELL)/d(mu) does not depend on the variance: K^T g_mu rides on the row-quadratic kernel's K tiles
+                mu, gmu_early = o.mu_gmu_parts(yb, w["mu_part"], noise, 1.0 / Bg)
+            with self._sec("rowquad"):
+                o.o8_slice_rows(C, 64, w["Cd"], w["cexp"])
+                T = o.o8_rowquad_digits(Bl, M, w["Ad"], s, w["Cd"], w["cexp"], w["T"], q_part=w["q_part"], gvec=gmu_early,
+                                        du_part=w["du_part"])
+                du = o.o8_sum_partials(w["du_part"])
+            w["skip_count"].zero_()
+            acc, gmu, gv, _ = o.gauss_ell_parts(yb, mu, w["q_part"], s, noise, self.jitter_xx, 1e-6, 1.0 / Bg,
+                                                skip_count=w["skip_count"], skip_rows=w["skip_rows"])
+        else:
+            with self._sec("kxz_fwd"):
+                K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
+            with self._sec("rowquad"):
                 T, q = self._rowquad(K, C)
-        acc, gmu, gv, _ = o.gauss_ell(yb, mu, q, s, noise, self.jitter_xx, 1e-6, 1.0 / Bg)
+            acc, gmu, gv, _ = o.gauss_ell(yb, mu, q, s, noise, self.jitter_xx, 1e-6, 1.0 / Bg)
         ell = acc[0] / Bg
 
         # ---- KL and prior (replicated terms)
@@ -329,17 +361,14 @@ class SVGPGibbs:
         # backward on the main stream, which starts when the SYRK has finished.
         wsyrk_done = torch.cuda.Event() if (self._side is not None and self.overlap) else None
         with self._fork():
-            if i8_syrk:
-                self._join2()
-                du = du_box[0]
-            else:
-                with self._sec("colwsum"):
-                    du = o.colwsum(K, w=gmu)
             with self._sec("wsyrk"):
-                # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
-                if i8_syrk:
-                    dC = o.wsyrk_i8(K, gv, acc[2:3], float(Bl), prepared=True)
+                if digits:
+                    # every unclamped row has the same weight w0 = acc[3]; clamped rows (normally none) are removed again
+                    dC = o.o8_syrk_digits(Bl, M, w["Ad"], s, w["syrk_part"], w0=acc[3:4], skip_count=w["skip_count"],
+                                          skip_rows=w["skip_rows"])
                 else:
+                    du = o.colwsum(K, w=gmu)
+                    # gv is constant unless a variance was clamped: acc[2] counts the unclamped rows (decided on the device)
                     dC = o.wsyrk(K, w=gv, uniform_count=acc[2:3], uniform_target=float(Bl))
             if wsyrk_done is not None:
                 wsyrk_done.record()
@@ -430,7 +459,7 @@ class SVGPGibbs:
         g["raw_noise"].copy_(-(dnoise * torch.sigmoid(p["raw_noise"])).reshape(1))
         self.grad[-2] = -elbo_local.reshape(())
         sec_m3.__exit__()
-        self.last = dict(info=zz["info"], ell=ell, kl=kl, log_prior=lp, mu=mu, q=q)
+        self.last = dict(info=zz["info"], ell=ell, kl=kl, log_prior=lp, mu=mu)
         return self.grad[-2]
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -472,8 +501,7 @@ class SVGPGibbs:
             self.loss_and_grad(self._gx, self._gy, world_size, B_global)
             if world_size == 1:
                 self.adam_step(lr)
-        # the graph holds raw pointers into the cached slice workspaces of the int8 GEMMs: keep them alive with the graph
-        self._graph_keepalive = list(getattr(self.o, "_I8_WORK", {}).values())
+        # (the graph holds raw pointers into self._i8_bufs, which live as long as the model)
         for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
             t.copy_(s)
         self.step_count = int(self.step_dev.item())
@@ -504,14 +532,25 @@ class SVGPGibbs:
         mean = torch.empty(n, dtype=torch.float64, device=self.dev)
         var = torch.empty(n, dtype=torch.float64, device=self.dev)
         K = T = None
+        digits = self._digits_mode()
+        if digits:
+            w0 = self._digit_buffers(min(chunk, n))
+            o.o8_slice_rows(zz["C"], 64, w0["Cd"], w0["cexp"])
         for lo in range(0, n, chunk):
             xc = xs[lo:lo + chunk].contiguous()
             fx = self._field_apply(xc, fc)
-            if K is None or K.shape[0] != xc.shape[0]:
-                K = torch.empty(xc.shape[0], self.M, dtype=torch.float64, device=self.dev)
-                T = torch.empty_like(K)
-            _, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"], out=K)
-            _, q = self._rowquad(K, zz["C"], T=T)
+            nc = xc.shape[0]
+            if digits:
+                w = self._digit_buffers(nc)
+                self._kernel_fwd_digits(xc, fx, p["Z"], fz, s, zz["u"], w)
+                o.o8_rowquad_digits(nc, self.M, w["Ad"], s, w0["Cd"], w0["cexp"], w["T"], q_part=w["q_part"])
+                mu, q = w["mu_part"].sum(0), w["q_part"].sum(0)
+            else:
+                if K is None or K.shape[0] != nc:
+                    K = torch.empty(nc, self.M, dtype=torch.float64, device=self.dev)
+                    T = torch.empty_like(K)
+                _, mu = self._kernel_fwd(xc, fx, p["Z"], fz, s, u=zz["u"], out=K)
+                _, q = self._rowquad(K, zz["C"], T=T)
             mean[lo:lo + chunk] = mu
             var[lo:lo + chunk] = (s + self.jitter_xx + q).clamp_min(1e-6)
         return mean, var
