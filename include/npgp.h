@@ -157,12 +157,12 @@ int npgp_rbfper_bwd(int n1, int n2, const double* t1, const double* t2, const do
 /* ---- exact FP64 contractions on the integer tensor cores (csrc/oz8.cu, csrc/oz8.cuh) ----------------------------------
  * Replaces the reference's dense n x M x M products: k_ux1.matmul(inv_root) and the Woodbury terms
  * (models/gibbs_kernels.py:222-232), A^T (S - I) A of the whitened VariationalStrategy (models/dgps.py:25-35 through
- * GPyTorch) and Phi = Kzx Kxz of the SGPR objective.  Every operand entry is the 56-bit integer rint(x 2^(55-e)) cut into
- * its 7 bytes (top byte signed, the others unsigned), e a power-of-two exponent per row or per matrix; the 28 byte
- * products with p + q <= 6 are accumulated exactly in int32 by tcgen05.mma kind::i8 and recombined in the epilogue.
+ * GPyTorch) and Phi = Kzx Kxz of the SGPR objective.  Every operand entry is the integer rint(x 2^(54-e)) written as 7
+ * signed base-256 digits, e a power-of-two exponent per row or per matrix; the 28 digit products with p + q <= 6 are
+ * accumulated exactly in int32 by tcgen05.mma kind::i8 (S8 x S8) and recombined in the epilogue.
  * Results equal the FP64 product to its own rounding bound and are bit-exact on integer-valued data.
  *
- * General operands (contract of npgp_rowquad / npgp_wsyrk): C symmetric, M % 64 == 0 (SYRK: M % 128 == 0), M <= 4608,
+ * General operands (contract of npgp_rowquad / npgp_wsyrk): C symmetric, M % 64 == 0 (SYRK: M % 128 == 0), M <= 16384,
  * T 16-byte aligned with even ldt.  work: the *_workspace_bytes(n, M) bytes of device memory (digit planes, exponents,
  * SYRK chunk partials).  The SYRK adds its row chunks in a fixed order: bitwise reproducible. */
 long npgp_rowquad_i8_workspace_bytes(int n, int M);

@@ -97,6 +97,8 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = restype
+        if os.environ.get("NPGP_O8_COLLECTOR") == "0":  # measurement / debugging switch (see npgp_o8_set_collector)
+            handle.npgp_o8_set_collector(0)
         _lib = handle
     return _lib
 

@@ -1,8 +1,8 @@
 // Gibbs cross-covariance tiles emitted directly as byte-digit planes for the int8 tensor-core contractions (oz8.cu):
 // K(X,Z) = scale * Gibbs kernel is evaluated pair by pair in FP64 exactly as in gibbs_diag.cu / gibbs_full.cu (reference
 // models/gibbs_kernels.py:154-162, models/multivariate_gibbs_kernel.py:101-150, models/sparse_multivariate_gibbs_kernel.py:
-// 105-154), but instead of 8 bytes of FP64 per pair the kernel stores the 7 bytes of y = rint(K_ij 2^(55-e)), e = exponent
-// of the outputscale (0 <= K_ij <= scale), in the row layout of oz8.cuh.  The N x M matrix then never exists in FP64: the
+// 105-154), but instead of 8 bytes of FP64 per pair the kernel stores the 7 signed base-256 digits of y = rint(K_ij 2^(54-e)),
+// e = exponent of the outputscale (0 <= K_ij <= scale), in the row layout of oz8.cuh.  The N x M matrix then never exists in FP64: the
 // row-quadratic product T = K C reads the planes K-major, the SYRK K^T K reads the same planes MN-major, and the row dot
 // rebuilds its K tile from them.  The fused matrix-vector product K u (predictive mean) is accumulated from the FP64 values.
 //
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_full_fwd_digits_kernel(
   const int nc = min(n2, c_begin + cols_per_cta) - c_begin;
   const double s = scale ? *scale : 1.0;
   const int e = o8_exponent_of_scale(s);
-  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(55 - e);
+  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(O8_FRAC - e);
   for (int c = threadIdx.x; c < nc; c += GD_ROWS) {
     const int j = c_begin + c;
     double Sj[P];
@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_full_fwd_digits_kernel(
   const double qi = (r < n1) ? sqrt(sqrt(sym_det<d>(Si))) : 0.0;  // a padded row evaluates to K = 0: zero digits
   __syncthreads();
   const int nks = n2 / O8_KS;
-  int8_t* rbase = digits + (long)(r / O8_BM) * nks * O8_A_STAGE + ((r % O8_BM) / 8) * 128 + (r % 8) * 16;
   double acc = 0.0;
   for (int c0 = 0; c0 < nc; c0 += 16) {
     long long y[16];
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_full_fwd_digits_kernel(
       if (HAS_U) acc = fma(k, col[d + P + 1], acc);
     }
     const int jg = c_begin + c0;
-    o8_store_digits(y, rbase + (long)(jg / O8_KS) * O8_A_STAGE + ((jg % O8_KS) / 16) * (O8_BM * 16), 2L * (O8_BM * 16));
+    o8_store_digits(y, digits + o8_a_offset(r, jg, nks), (long)nks * O8_A_PLANE);
   }
   if (HAS_U && r < n1) Ku_part[(long)blockIdx.y * ku_stride + r] = acc;
 }
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_diag_fwd_digits_kernel(
   const int nc = min(n2, c_begin + cols_per_cta) - c_begin;
   const double s = scale ? *scale : 1.0;
   const int e = o8_exponent_of_scale(s);
-  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(55 - e);
+  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(O8_FRAC - e);
   for (int c = threadIdx.x; c < nc; c += GD_ROWS) {
     const int j = c_begin + c;
     double prod = 1.0;
@@ -135,7 +134,6 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_diag_fwd_digits_kernel(
   const double ci = (r < n1) ? sqrt(prod) : 0.0;
   __syncthreads();
   const int nks = n2 / O8_KS;
-  int8_t* rbase = digits + (long)(r / O8_BM) * nks * O8_A_STAGE + ((r % O8_BM) / 8) * 128 + (r % 8) * 16;
   double acc = 0.0;
   for (int c0 = 0; c0 < nc; c0 += 16) {
     long long y[16];
@@ -154,7 +152,7 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_diag_fwd_digits_kernel(
       if (HAS_U) acc = fma(k, col[2 * D + 1], acc);
     }
     const int jg = c_begin + c0;
-    o8_store_digits(y, rbase + (long)(jg / O8_KS) * O8_A_STAGE + ((jg % O8_KS) / 16) * (O8_BM * 16), 2L * (O8_BM * 16));
+    o8_store_digits(y, digits + o8_a_offset(r, jg, nks), (long)nks * O8_A_PLANE);
   }
   if (HAS_U && r < n1) Ku_part[(long)blockIdx.y * ku_stride + r] = acc;
 }

@@ -4,25 +4,27 @@
 // replacing the reference's dense products k_ux1.matmul(inv_root) / A^T (S - I) A (models/gibbs_kernels.py:222-232 and the
 // whitened VariationalStrategy driven by models/dgps.py:25-35).  B200 has no FP64 tcgen05 kind and DMMA peaks at 37 TFLOP/s.
 //
-// Arithmetic (oz8.cuh): each operand entry is the 56-bit integer y = rint(x 2^(55-e)) with a power-of-two scale per row (or
-// per matrix), cut into its 7 bytes a_0 (signed) .. a_6 (unsigned).  Then
-//     T_ij = 2^(e_i + f_j - 14) sum_{t=0..6} 2^(-8t) G_t,     G_t = sum_{p+q=t} (a_p c_q^T)_ij   exact in int32,
-// 28 digit products (round 1: 8 seven-bit digits, 36 products); the dropped terms t >= 7 are below 2^-53 of
+// Arithmetic (oz8.cuh): each operand entry is the integer y = rint(x 2^(54-e)) with a power-of-two scale per row (or per
+// matrix), written as 7 signed base-256 digits.  Then
+//     T_ij = 2^(e_i + f_j - 12) sum_{t=0..6} 2^(-8t) G_t,     G_t = sum_{p+q=t} (a_p c_q^T)_ij   exact in int32,
+// 28 digit products (round 1: 8 seven-bit digits, 36 products); the dropped terms t >= 7 are below 2^-52 of
 // (row max)(column max) per contraction entry, the size of the FP64 rounding bound itself.  The seven G_t live in seven
-// TMEM accumulators of 128 lanes x 64 columns.  Signedness is per MMA (instruction descriptor): S8 for a top digit, U8 else.
+// TMEM accumulators of 128 lanes x 64 columns.
 //
 // Data flow.  Digit planes arrive in the row layout of oz8.cuh -- written by the slicing kernels below for arbitrary
 // operands, or directly by the Gibbs tile kernels (gibbs_digits.cu) for K(X,Z), which then never exists in FP64.  Warp
-// roles per CTA (one persistent CTA per SM): warp 0 producer (cp.async.bulk global -> shared, mbarrier completion), warp 1
-// MMA issuer (one elected lane, 28 MMAs per 32-byte k-step, A-operand collector reuse across the B digits, tcgen05.commit
-// frees the stage), warps 2-5 epilogue (tcgen05.ld, integer recombination, power-of-two scaling, fused row dot / column
-// sums against the K tile rebuilt from the digits while the MMAs run).
+// roles per CTA (one persistent CTA per SM): warp 0 producer (cp.async.bulk / TMA tensor copies global -> shared, mbarrier
+// completion), warp 1 MMA issuer (one elected lane, 28 MMAs per 32-byte k-step, A-operand collector reuse across the B
+// digits, tcgen05.commit frees the stage), warps 2-5 epilogue (tcgen05.ld, integer recombination, power-of-two scaling,
+// fused row dot / column sums against the K tile rebuilt from the digits while the MMAs run).
 // The SYRK contracts over the ROWS of K.  With a matrix-wide scale it reads the same row-layout planes MN-major
-// (instruction descriptor a_major = b_major = 1; verified by tools/probes/umma_i8_probe2.cu); with per-column scales (general
-// operands) it reads transposed planes written by o8_slice_t_kernel.  Chunks of <= 4096 rows keep int32 exact; every
-// (tile, chunk) item stores its FP64 partial and a finishing kernel adds the chunks in a fixed order (no FP64 atomics:
-// results are bitwise reproducible).
+// (instruction descriptor a_major = b_major = 1; verified by tools/probes/umma_i8_probe2.cu), each operand tile fetched by
+// one 5-D TMA box; with per-column scales (general operands) it reads transposed planes written by o8_slice_t_kernel.
+// Chunks of <= 8192 rows keep int32 exact; every (tile, chunk) item stores its FP64 partial and a finishing kernel adds the
+// chunks in a fixed order (no FP64 atomics: results are bitwise reproducible).
 // Descriptor encodings: cute/arch/mma_sm100_desc.hpp of the vendored CUTLASS.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cstring>
 #include <cstdint>
 
 #include "common.cuh"
@@ -34,7 +36,7 @@ constexpr int O8_THREADS = 192;
 constexpr int O8_RQ_STAGES = 3;
 constexpr int O8_SY_STAGES = 4;
 constexpr int O8_KLD = O8_BN + 2;            // leading dimension (doubles) of the staged K tile
-constexpr int O8_CHUNK_STAGES = 128;         // <= 4096 contraction rows per int32 accumulation of the SYRK
+constexpr int O8_CHUNK_STAGES = 256;         // <= 8192 contraction rows per int32 accumulation of the SYRK
 constexpr int O8_RQ_SMEM = O8_RQ_STAGES * (O8_A_STAGE + O8_B_STAGE) + O8_BM * O8_KLD * 8 + 1024;
 constexpr int O8_SY_SMEM = O8_SY_STAGES * (O8_A_STAGE + O8_B_STAGE) + 1024;
 
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(512, 2) o8_slice_rows_kernel(int R, int Rpad, 
   __syncthreads();
   if (r >= Rpad) return;
   const int e = sexp[rr];
-  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(55 - e);
+  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(O8_FRAC - e);
   const long blk = (long)(r / BR) * nks;
   const int rin = ((r % BR) / 8) * 128 + (r % 8) * 16;
   for (int c = ch; c < nch; c += 64) {
@@ -100,7 +102,10 @@ __global__ void __launch_bounds__(512, 2) o8_slice_rows_kernel(int R, int Rpad, 
     long long y[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = (e == O8_POISON) ? 0ll : o8_quantise(v[j], sc);
-    o8_store_digits(y, out + ((blk + c / 2) * O8_NS * 2 + (c & 1)) * (long)(BR * 16) + rin, 2L * (BR * 16));
+    if (BR == O8_BM)  // A-type layout: digit-major inside the row block
+      o8_store_digits(y, out + o8_a_offset(r, c * 16, nks), (long)nks * O8_A_PLANE);
+    else              // B-type layout: stage-contiguous
+      o8_store_digits(y, out + ((blk + c / 2) * O8_NS * 2 + (c & 1)) * (long)(BR * 16) + rin, 2L * (BR * 16));
   }
 }
 
@@ -143,12 +148,11 @@ __global__ void __launch_bounds__(256) o8_slice_t_kernel(int R, int Kd, const do
   const int j = threadIdx.x & 127, half = threadIdx.x >> 7;
   const int gj = jb * 128 + j;
   const int e = (gj < Kd) ? expo[gj] : 0;
-  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(55 - e);
+  const double sc = (e == O8_POISON) ? 0.0 : o8_pow2(O8_FRAC - e);
   long long y[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) y[k] = (e == O8_POISON) ? 0ll : o8_quantise(tile[half * 16 + k][j], sc);
-  int8_t* base = out + (((long)jb * nks + ks) * O8_NS * 2 + half) * (long)(O8_BM * 16) + (j / 8) * 128 + (j % 8) * 16;
-  o8_store_digits(y, base, 2L * (O8_BM * 16));
+  o8_store_digits(y, out + o8_a_offset((long)jb * O8_BM + j, ks * O8_KS + half * 16, nks), (long)nks * O8_A_PLANE);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -179,6 +183,14 @@ __device__ __forceinline__ void o8_bulk_g2s(void* dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(o8_smem(dst)),
                "l"(src), "r"(bytes), "r"(o8_smem(b))
                : "memory");
+}
+// one 5-D TMA box (tile mode) global -> shared, completion on the mbarrier
+__device__ __forceinline__ void o8_tma_5d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, uint64_t* b) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          o8_smem(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(o8_smem(b))
+      : "memory");
 }
 __device__ __forceinline__ void o8_commit(uint64_t* b) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(o8_smem(b)) : "memory");
@@ -214,7 +226,7 @@ O8_DEFINE_MMA(o8_mma_use, ".collector::a::use")
 O8_DEFINE_MMA(o8_mma_last, ".collector::a::lastuse")
 
 // The 28 digit products of one k-step: A digit p (descriptor a_lo + p * a_plane16) against B digits q = 0 .. 6 - p, into
-// accumulator p + q.  The A operand of a fixed p is reused across its B digits (collector hints).  Signedness per product.
+// accumulator p + q.  The A operand of a fixed p is reused across its B digits (collector hints).
 template <bool COLL>
 __device__ __forceinline__ void o8_issue_kstep(uint32_t tmem, uint32_t a_lo, uint32_t a_hi, uint32_t a_plane16, uint32_t b_lo,
                                                uint32_t b_hi, uint32_t b_plane16, uint32_t idesc_base, uint32_t first) {
@@ -224,7 +236,7 @@ __device__ __forceinline__ void o8_issue_kstep(uint32_t tmem, uint32_t a_lo, uin
 #pragma unroll
     for (int qq = 0; qq < O8_NS - p; ++qq) {
       const uint64_t db = o8_desc(b_lo + qq * b_plane16, b_hi);
-      const uint32_t idesc = idesc_base | (p == 0 ? (1u << 7) : 0u) | (qq == 0 ? (1u << 10) : 0u);
+      const uint32_t idesc = idesc_base;  // every digit is signed: S8 x S8
       const uint32_t d = tmem + (uint32_t)((p + qq) * O8_BN);
       const uint32_t acc = p > 0 ? 1u : first;
       if (!COLL || p == O8_NS - 1) o8_mma_plain(d, da, db, idesc, acc);
@@ -294,32 +306,33 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
-    // ===== producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_empty = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int rb = tile / n_cb, cb = tile % n_cb;
-        const int8_t* a = As + (long)rb * nks * O8_A_STAGE;
-        const int8_t* b = Bs + (long)cb * nks * O8_B_STAGE;
-        for (int ks = 0; ks < nks; ++ks) {
-          const long long c0 = dbg ? clock64() : 0;
-          o8_mbar_wait(&empty[stage], phase ^ 1);
-          if (dbg) w_empty += clock64() - c0;
-          o8_mbar_expect_tx(&full[stage], O8_A_STAGE + O8_B_STAGE);
-          o8_bulk_g2s(sA + stage * O8_A_STAGE, a + (long)ks * O8_A_STAGE, O8_A_STAGE, &full[stage]);
+    // ===== producer: lanes 0..6 copy the seven digit planes of the A block's k-step (4 KB each), lane 7 the B stage =====
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_empty = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int rb = tile / n_cb, cb = tile % n_cb;
+      const int8_t* a = As + ((long)rb * O8_NS + lane) * nks * O8_A_PLANE;  // lane = digit
+      const int8_t* b = Bs + (long)cb * nks * O8_B_STAGE;
+      for (int ks = 0; ks < nks; ++ks) {
+        const long long c0 = dbg ? clock64() : 0;
+        o8_mbar_wait(&empty[stage], phase ^ 1);
+        if (dbg) w_empty += clock64() - c0;
+        if (lane == 0) o8_mbar_expect_tx(&full[stage], O8_A_STAGE + O8_B_STAGE);
+        __syncwarp();
+        if (lane < O8_NS)
+          o8_bulk_g2s(sA + stage * O8_A_STAGE + lane * O8_A_PLANE, a + (long)ks * O8_A_PLANE, O8_A_PLANE, &full[stage]);
+        else if (lane == O8_NS)
           o8_bulk_g2s(sB + stage * O8_B_STAGE, b + (long)ks * O8_B_STAGE, O8_B_STAGE, &full[stage]);
-          if (++stage == O8_RQ_STAGES) { stage = 0; phase ^= 1; }
-        }
+        if (++stage == O8_RQ_STAGES) { stage = 0; phase ^= 1; }
       }
-      if (dbg && blockIdx.x == 0) dbg[0] = w_empty;
     }
+    if (dbg && blockIdx.x == 0 && lane == 0) dbg[0] = w_empty;
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow), one elected lane issues =====
     const bool leader = o8_elect_one();
-    // c_format S32 (2) @4, a/b signedness @7/@10 per product, both K-major, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (2u << 4) | ((uint32_t)(O8_BN >> 3) << 17) | ((uint32_t)(O8_BM >> 4) << 24);
+    // c_format S32 (2) @4, a/b format signed 8 bit (1) @7/@10, both K-major, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O8_BN >> 3) << 17) | ((uint32_t)(O8_BM >> 4) << 24);
     constexpr uint32_t kHi = (128u >> 4) | (1u << 14);  // stride byte offset 128 (next 8 rows), descriptor version 1
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -376,14 +389,14 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
           }
         } else {
           // rebuild the thread's row of the tile from the digit planes (the two k-steps that hold these 64 columns)
-          const double asc = (er == O8_POISON) ? __longlong_as_double(0x7FF8000000000000ll) : o8_pow2(er - 55);
-          const int8_t* ab = As + ((long)rb * nks + 2 * cb) * O8_A_STAGE + (rloc / 8) * 128 + (rloc % 8) * 16;
+          const double asc = (er == O8_POISON) ? __longlong_as_double(0x7FF8000000000000ll) : o8_pow2(er - O8_FRAC);
+          const int8_t* ab = As + o8_a_offset((long)rb * O8_BM + rloc, cb * O8_BN, nks);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {  // (k-step, 16-column half)
             uint4 dg[O8_NS];
 #pragma unroll
             for (int p = 0; p < O8_NS; ++p)
-              dg[p] = *reinterpret_cast<const uint4*>(ab + (long)(h >> 1) * O8_A_STAGE + (p * 2 + (h & 1)) * (O8_BM * 16));
+              dg[p] = *reinterpret_cast<const uint4*>(ab + ((long)p * nks + (h >> 1)) * O8_A_PLANE + (h & 1) * (O8_BM * 16));
             double* dst = sK + rloc * O8_KLD + h * 16;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
@@ -414,7 +427,7 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       o8_mbar_wait(&acc_full, acc_phase);
       if (dbg) w_accfull += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double rs = o8_scale_or_nan(er, -38);  // 2^(e_i - 14 - 24)
+      const double rs = o8_scale_or_nan(er, -36);  // 2^(e_i - 12 - 24)
       const double* krow = sK + rloc * O8_KLD;
       double qsum = 0.0;
       for (int c0i = 0; c0i < O8_BN; c0i += 8) {
@@ -459,7 +472,10 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
 
 // ---------------------------------------------------------------------------------------------------------------------
 // SYRK partials: part[chunk][M x M] (upper 128 x 64 tiles) = X^T X over the rows of one chunk.
-//   MN = true : Xs = row-layout planes of X itself (R x M, BR = 128), one matrix-wide scale (*x_scale); operands MN-major.
+//   MN = true : row-layout planes of X itself (R x M), one matrix-wide scale (*x_scale); operands MN-major.  A stage holds
+//               32 rows i of X: the A tile (128 columns j) and the B tile (64 columns) are 5-D TMA boxes (tmA, tmB) over
+//               [8-byte words of a 2048-byte plane | 16-byte half | column k-step | digit | row block] that land in shared
+//               memory as [digit][16-column group][4 core matrices of 8 rows x 16 bytes].
 //   MN = false: Xs = transposed planes (operand rows = columns of X, o8_slice_t_kernel), per-column exponents ex; K-major.
 // Work item = (chunk, tile), chunk-major so that the CTAs running together read the same rows (L2 reuse).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -467,7 +483,7 @@ template <bool MN, bool COLL>
 __global__ void __launch_bounds__(O8_THREADS, 1)
 o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restrict__ Xs, const int* __restrict__ ex,
                const double* __restrict__ x_scale, const double* __restrict__ uniform_count, double uniform_target,
-               double* __restrict__ part) {
+               double* __restrict__ part, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   if (uniform_count && *uniform_count != uniform_target) return;  // unequal weights: handled by the correction kernels
   extern __shared__ __align__(1024) uint8_t o8_sm[];
   uint8_t* sA = o8_sm;
@@ -513,7 +529,7 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
-    // ===== producer: all 32 lanes issue bulk copies (the MN-major tile is a gather of 84 pieces of 512 bytes) =====
+    // ===== producer =====
     int stage = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -526,31 +542,30 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
         uint8_t* dA = sA + stage * O8_A_STAGE;
         uint8_t* dB = sB + stage * O8_B_STAGE;
         if (MN) {
-          // rows ks*32 .. +31 of X: row block ib = ks / 4, core-matrix rows m8_0 = (ks % 4) * 4 .. +3 (512 contiguous bytes)
-          const int8_t* src0 = Xs + (long)(ks >> 2) * nks_cols * O8_A_STAGE + (ks & 3) * 512;
-          for (int idx = lane; idx < 84; idx += 32) {
-            const bool isA = idx < 56;
-            const int id2 = isA ? idx : idx - 56;
-            const int per = isA ? 8 : 4;                    // (column k-step, half) pieces per digit
-            const int p = id2 / per, rem = id2 % per;
-            const int js = (isA ? 4 * rb : 2 * cb) + (rem >> 1), cj = rem & 1;
-            const int8_t* src = src0 + ((long)js * O8_NS + p) * (2 * O8_BM * 16) + cj * (O8_BM * 16);
-            uint8_t* dst = (isA ? dA + p * 4096 : dB + p * 2048) + rem * 512;
-            o8_bulk_g2s(dst, src, 512, &full[stage]);
-          }
+          // rows ks*32 .. +31 of X = row block ks / 4, core-matrix rows (ks % 4) * 4 .. +3 = 8-byte words (ks % 4) * 64 .. +63
+          // of every plane; box = (64 words, 2 halves, 4 | 2 column k-steps, 7 digits, 1 row block)
+          if (lane == 0) o8_tma_5d(dA, &tmA, (ks & 3) * 64, 0, 4 * rb, 0, ks >> 2, &full[stage]);
+          else if (lane == 1) o8_tma_5d(dB, &tmB, (ks & 3) * 64, 0, 2 * cb, 0, ks >> 2, &full[stage]);
         } else {
-          const int8_t* a = Xs + ((long)rb * nks_total + ks) * O8_A_STAGE;
-          const int8_t* b = Xs + ((long)(cb >> 1) * nks_total + ks) * O8_A_STAGE + (cb & 1) * (O8_BN * 16);
-          if (lane == 0) o8_bulk_g2s(dA, a, O8_A_STAGE, &full[stage]);
-          else if (lane <= 2 * O8_NS)  // (digit, half) pieces of the B operand: 64 rows x 16 bytes each
-            o8_bulk_g2s(dB + (lane - 1) * (O8_BN * 16), b + (long)(lane - 1) * (O8_BM * 16), O8_BN * 16, &full[stage]);
+          // A: the seven digit planes of (row block rb, k-step ks), 4 KB each; B: 64 of the 128 rows of (block cb / 2): per
+          // digit and 16-byte half one piece of 64 rows x 16 bytes
+          if (lane < O8_NS)
+            o8_bulk_g2s(dA + lane * O8_A_PLANE, Xs + (((long)rb * O8_NS + lane) * nks_total + ks) * O8_A_PLANE, O8_A_PLANE,
+                        &full[stage]);
+          else if (lane < 3 * O8_NS) {
+            const int pp = lane - O8_NS, pd = pp >> 1, half = pp & 1;
+            o8_bulk_g2s(dB + pp * (O8_BN * 16),
+                        Xs + (((long)(cb >> 1) * O8_NS + pd) * nks_total + ks) * O8_A_PLANE + half * (O8_BM * 16) +
+                            (cb & 1) * (O8_BN * 16),
+                        O8_BN * 16, &full[stage]);
+          }
         }
         if (++stage == O8_SY_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     const bool leader = o8_elect_one();
-    uint32_t idesc = (2u << 4) | ((uint32_t)(O8_BN >> 3) << 17) | ((uint32_t)(O8_BM >> 4) << 24);
+    uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O8_BN >> 3) << 17) | ((uint32_t)(O8_BM >> 4) << 24);
     if (MN) idesc |= (1u << 15) | (1u << 16);
     // K-major: LBO = distance of the two 16-byte k halves, SBO = 128 (next 8 rows)
     // MN-major: LBO = 128 (next 8 contraction rows), SBO = 512 (next 16 operand rows)
@@ -591,7 +606,7 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
       asm volatile("bar.sync 1, 128;" ::: "memory");
       o8_mbar_wait(&acc_full, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double rs = o8_scale_or_nan(MN ? e_all : ex[row], -38);
+      const double rs = o8_scale_or_nan(MN ? e_all : ex[row], -36);
       double* prow = part + (long)chunk * M * M + (long)row * M + cb * O8_BN;
       for (int c0i = 0; c0i < O8_BN; c0i += 8) {
         uint32_t g[O8_NS][8];
@@ -616,13 +631,12 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-// one entry of a row-layout digit matrix (rows in blocks of 128) as a double, without the power-of-two scale
+// one entry of a row-layout digit matrix (A-type planes) as a double, without the power-of-two scale
 __device__ __forceinline__ double o8_entry(const int8_t* __restrict__ digits, int nks, int r, int k) {
-  const int8_t* b = digits + ((long)(r / O8_BM) * nks + k / O8_KS) * O8_A_STAGE + ((k % O8_KS) / 16) * (O8_BM * 16) +
-                    ((r % O8_BM) / 8) * 128 + (r % 8) * 16 + (k % 16);
-  long long y = (long long)b[0];  // signed top digit
+  const int8_t* b = digits + o8_a_offset(r, k & ~15, nks) + (k & 15);
+  long long y = 0;
 #pragma unroll
-  for (int p = 1; p < O8_NS; ++p) y = y * 256 + (long long)(uint8_t)b[(long)p * (2 * O8_BM * 16)];
+  for (int p = 0; p < O8_NS; ++p) y = y * 256 + (long long)b[(long)p * nks * O8_A_PLANE];  // seven signed digits
   return (double)y;
 }
 
@@ -644,7 +658,7 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int n_chunks
     const int ns = *skip_count;
     if (ns > 0) {
       const int e = o8_exponent_of_scale(*x_scale);
-      const double sc2 = o8_pow2(2 * (e - 55));
+      const double sc2 = o8_pow2(2 * (e - O8_FRAC));
       double corr = 0.0;
       for (int t = 0; t < ns; ++t) {
         const int i = skip_rows[t];
@@ -818,7 +832,7 @@ static int rowquad_i8_impl(int n, int M, const double* K, long ldk, const double
 }
 
 // T (n x M) = K (n x M) @ C (M x M, symmetric);  q[i] += sum_j T_ij K_ij (q zeroed by the caller; NULL to skip).
-// M must be a multiple of 64 (and <= 4608).  Replaces npgp_rowquad on the integer tensor-core path.
+// M must be a multiple of 64 (and <= 16384).  Replaces npgp_rowquad on the integer tensor-core path.
 extern "C" int npgp_rowquad_i8(int n, int M, const double* K, long ldk, const double* C, long ldc, double* T, long ldt,
                                double* q, void* work, long work_bytes, cudaStream_t stream) {
   return rowquad_i8_impl(n, M, K, ldk, C, ldc, T, ldt, q, work, work_bytes, stream, true, true);
@@ -844,6 +858,32 @@ extern "C" long npgp_o8_syrk_part_bytes(int n, int M) {
   return (long)n_chunks * M * M * (long)sizeof(double);
 }
 
+// 5-D tensor map over the A-type digit planes of X (n_rb row blocks x M columns) for the MN-major SYRK tiles, in units of
+// 8-byte words: [256 words of a 2048-byte plane | 2 halves | M/32 column k-steps | 7 digits | n_rb row blocks];
+// box = (64 words = 32 rows, 2, box_ksteps, 7, 1).  The encoder lives in the driver: fetched once per process.
+typedef CUresult (*o8_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int o8_make_syrk_map(CUtensorMap* tm, const int8_t* digits, int M, int n_rb, int box_ksteps) {
+  static o8_encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    NPGP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) return NPGP_EUNSUPPORTED;
+    encode = reinterpret_cast<o8_encode_fn>(fn);
+  }
+  const cuuint64_t nks = (cuuint64_t)(M / O8_KS);
+  const cuuint64_t dims[5] = {256, 2, nks, (cuuint64_t)O8_NS, (cuuint64_t)n_rb};
+  const cuuint64_t strides[4] = {2048, (cuuint64_t)O8_A_PLANE, nks * O8_A_PLANE, (cuuint64_t)O8_NS * nks * O8_A_PLANE};  // bytes, dims 1..4
+  const cuuint32_t box[5] = {64, 2, (cuuint32_t)box_ksteps, (cuuint32_t)O8_NS, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, const_cast<int8_t*>(digits), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NPGP_OK : NPGP_EUNSUPPORTED;
+}
+
 template <bool MN>
 static int o8_syrk_launch(int M, int nks, const int8_t* Xs, const int* ex, const double* x_scale, double alpha,
                           const double* w0_dev, const double* uniform_count, double uniform_target, int accumulate,
@@ -851,6 +891,15 @@ static int o8_syrk_launch(int M, int nks, const int8_t* Xs, const int* ex, const
                           cudaStream_t stream) {
   NPGP_CUDA(cudaFuncSetAttribute(o8_syrk_kernel<MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_SY_SMEM));
   NPGP_CUDA(cudaFuncSetAttribute(o8_syrk_kernel<MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, O8_SY_SMEM));
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  if (MN) {
+    int rc = o8_make_syrk_map(&tmA, Xs, M, nks / 4, 4);
+    if (rc) return rc;
+    rc = o8_make_syrk_map(&tmB, Xs, M, nks / 4, 2);
+    if (rc) return rc;
+  }
   const int n_tiles = o8_syrk_tiles(M);
   int spc;
   const int n_chunks = o8_syrk_chunks(nks, n_tiles, &spc);
@@ -858,14 +907,14 @@ static int o8_syrk_launch(int M, int nks, const int8_t* Xs, const int* ex, const
   const int grid = items < kNumSMs ? items : kNumSMs;
   if (g_o8_collector)
     o8_syrk_kernel<MN, true><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, Xs, ex, x_scale, uniform_count,
-                                                                      uniform_target, part);
+                                                                      uniform_target, part, tmA, tmB);
   else
     o8_syrk_kernel<MN, false><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, Xs, ex, x_scale, uniform_count,
-                                                                       uniform_target, part);
+                                                                       uniform_target, part, tmA, tmB);
   NPGP_LAUNCH_CHECK();
   dim3 grd(ceil_div(M, 32), ceil_div(M, 8));
   o8_syrk_finish_kernel<<<grd, 256, 0, stream>>>(M, n_chunks, part, alpha, w0_dev, uniform_count, uniform_target, accumulate,
-                                                 Out, ldo, skip_count, skip_rows, Xs, x_scale);
+                                                 Out, ldo, skip_count, skip_rows, MN ? Xs : nullptr, x_scale);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

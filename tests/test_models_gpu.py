@@ -16,9 +16,9 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
 
 
-def make_prior(D, os=1.0, lam=1.3, mean=0.3, device="cuda"):
+def make_prior(D, os=1.0, lam=1.3, mean=0.3, device="cuda", active_dims=None):
     from nonstationary_precip_b200.models.gibbs_kernels import LogNormalPriorProcess
-    prior = LogNormalPriorProcess(input_dim=D).to(device).double()
+    prior = LogNormalPriorProcess(input_dim=D, active_dims=active_dims).to(device).double()
     # the reference's way of setting the hyper-parameters (experiments/spatial_exp.py:159-167)
     prior.covar_module.outputscale = os * torch.ones_like(prior.covar_module.outputscale)
     prior.covar_module.base_kernel.lengthscale = lam * torch.ones_like(prior.covar_module.base_kernel.lengthscale)
@@ -187,7 +187,7 @@ def test_spatio_temporal_nonstationary_objective_and_predict():
     x, xs = xa[perm[:n]], xa[perm[n:]]
     y = torch.sin(2 * math.pi * x[:, 0]) * torch.exp(-x[:, 1] ** 2) + 0.1 * torch.randn(n, generator=g)
     z = x[torch.randperm(n, generator=g)[:M]].clone()
-    prior = make_prior(2)
+    prior = make_prior(2, active_dims=(0, 1))  # as the reference's experiments/spatio_temporal_exp.py:111
     lik = GaussianLikelihood().cuda().double()
     model = SparseSpatioTemporal_Nonstationary(x.cuda(), y.cuda(), lik, prior, z.cuda(), num_dim=2).cuda().double()
     model.likelihood.noise = 0.05

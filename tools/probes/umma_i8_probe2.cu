@@ -60,7 +60,7 @@ __device__ __forceinline__ bool elect_one() {
 // mode 0: K-major (A: [r][k], core rows = r), a u8 / b s8
 // mode 1/2: MN-major, core rows = k; LBO/SBO assignment 1: LBO = K-group stride, SBO = MN-group stride; 2: swapped
 // mode 3: collector test (K-major, three B tiles of 64 rows -> three accumulators)
-__global__ void __launch_bounds__(128) probe(const uint8_t* A, const int8_t* B, int32_t* D, int mode) {
+__global__ void __launch_bounds__(128) probe(const uint8_t* A, const int8_t* B, int32_t* D, int mode, int a_signed, int b_signed) {
   __shared__ __align__(128) uint8_t sA[MM * KK];
   __shared__ __align__(128) int8_t sB[3 * NN * KK];
   __shared__ __align__(8) uint64_t mbar;
@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(128) probe(const uint8_t* A, const int8_t* B, 
   const uint32_t tbase = tmem_base;
   if (warp == 0) {
     if (elect_one()) {
-      // c S32, a unsigned (0), b signed (1)
-      uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(MM >> 4) << 24);
+      // c S32; a / b format: 0 = unsigned 8 bit, 1 = signed 8 bit
+      uint32_t idesc = (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(NN >> 3) << 17) |
+                       ((uint32_t)(MM >> 4) << 24);
       if (mode == 0) {
         mma_plain(tbase, make_desc(smem_u32(sA), MM * 16, 128), make_desc(smem_u32(sB), NN * 16, 128), idesc, 0);
       } else if (mode == 1 || mode == 2) {
@@ -219,24 +220,31 @@ int main() {
   cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice);
   const char* names[4] = {"K-major u8 x s8", "MN-major (LBO=K-group 128, SBO=MN-group 512)", "MN-major (LBO=512, SBO=128)",
                           "collector fill/use/lastuse"};
-  for (int mode = 0; mode < 4; ++mode) {
-    cudaMemset(dD, 0xff, sizeof(int32_t) * 3 * MM * NN);
-    probe<<<1, 128>>>(dA, dB, dD, mode);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 1; }
-    const int nb = mode == 3 ? 3 : 1;
-    std::vector<int32_t> hD(3 * MM * NN);
-    cudaMemcpy(hD.data(), dD, sizeof(int32_t) * 3 * MM * NN, cudaMemcpyDeviceToHost);
-    long bad = 0;
-    for (int t = 0; t < nb; ++t)
-      for (int i = 0; i < MM; ++i)
-        for (int j = 0; j < NN; ++j) {
-          int32_t ref = 0;
-          for (int k = 0; k < KK; ++k) ref += (int32_t)hA[i * KK + k] * (int32_t)hB[t * NN * KK + j * KK + k];
-          if (ref != hD[(t * MM + i) * NN + j]) ++bad;
-        }
-    printf("mode %d [%s]: %ld of %d entries wrong\n", mode, names[mode], bad, nb * MM * NN);
-  }
+  for (int mode = 0; mode < 4; ++mode)
+    for (int combo = 0; combo < (mode == 0 ? 4 : 1); ++combo) {
+      const int a_signed = mode == 0 ? (combo >> 1) : 0, b_signed = mode == 0 ? (combo & 1) : 1;
+      cudaMemset(dD, 0xff, sizeof(int32_t) * 3 * MM * NN);
+      probe<<<1, 128>>>(dA, dB, dD, mode, a_signed, b_signed);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mode %d: CUDA error %s\n", mode, cudaGetErrorString(e)); return 1; }
+      const int nb = mode == 3 ? 3 : 1;
+      std::vector<int32_t> hD(3 * MM * NN);
+      cudaMemcpy(hD.data(), dD, sizeof(int32_t) * 3 * MM * NN, cudaMemcpyDeviceToHost);
+      long bad = 0;
+      for (int t = 0; t < nb; ++t)
+        for (int i = 0; i < MM; ++i)
+          for (int j = 0; j < NN; ++j) {
+            int32_t ref = 0;
+            for (int k = 0; k < KK; ++k) {
+              const int32_t av = a_signed ? (int32_t)(int8_t)hA[i * KK + k] : (int32_t)hA[i * KK + k];
+              const int32_t bv = b_signed ? (int32_t)hB[t * NN * KK + j * KK + k] : (int32_t)(uint8_t)hB[t * NN * KK + j * KK + k];
+              ref += av * bv;
+            }
+            if (ref != hD[(t * MM + i) * NN + j]) ++bad;
+          }
+      printf("mode %d [%s] a %s x b %s: %ld of %d entries wrong\n", mode, names[mode], a_signed ? "s8" : "u8",
+             b_signed ? "s8" : "u8", bad, nb * MM * NN);
+    }
   long long* dout;
   cudaMalloc(&dout, 8 * sizeof(long long));
   cudaMemset(dout, 0, 8 * sizeof(long long));
