@@ -106,6 +106,12 @@ int npgp_set_gemm_config(int cfg);
 long npgp_potrf_workspace_bytes(int M);
 int npgp_potrf_inv_lower(int M, double* A, long lda, double* P, long ldp, void* work, long work_bytes, int* info,
                          npgp_stream_t stream);
+/* Same contract in ONE kernel launch (csrc/chol_flow.cu): every 64 x 64 tile of L and of L^-1 is a resident CTA that waits
+ * on per-tile flags, so a dependent panel step costs an L2 round trip instead of a kernel boundary and the inverse is
+ * assembled while the factorisation proceeds.  *info = -1 if a (bounded) dataflow wait timed out.  work: flags only. */
+long npgp_potrf_flow_workspace_bytes(int M);
+int npgp_potrf_inv_flow(int M, double* A, long lda, double* P, long ldp, void* work, long work_bytes, int* info,
+                        npgp_stream_t stream);
 
 /* ---- SVGP-Gibbs ELBO step: small kernels (GPyTorch VariationalELBO + GaussianLikelihood.expected_log_prob semantics
  * as driven by experiments/deepgp_spatial_bench.py:61,84-87) -------------------------------

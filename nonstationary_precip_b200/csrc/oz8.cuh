@@ -4,7 +4,7 @@
 // A real matrix X (R x Kd, rows padded to 128 or 64) with one power-of-two scale 2^e per row (or one for the whole matrix)
 // is stored as the integer y = rint(x 2^(54-e)), |y| <= 2^54, written in BALANCED base 256:
 //     x 2^-e = sum_{p=0..6} a_p 2^(-6-8p),      a_p in [-128, 127]   (all seven digits signed)
-// (digit p is byte 6-p of y + 0x0080808080808080 with the low six bytes' top bit flipped: two integer operations per word).
+// (digit p is byte 6-p of y + 0x0000808080808080 with the low six bytes' top bit flipped: two integer operations per word).
 // Seven signed digits carry 55 bits -- the same resolution relative to the row maximum as a double has relative to 1/4 of
 // its own value -- and need 28 digit products with p + q <= 6 where round 1's eight 7-bit digits needed 36.  Every MMA is
 // S8 x S8 with one constant instruction descriptor.
@@ -38,7 +38,7 @@ constexpr int O8_POISON = 1 << 20;                  // exponent marking a row / 
 constexpr int O8_EMIN = -960;                       // exponents are clamped here so that 2^(54-e) stays a normal double
 constexpr int O8_FRAC = 54;                         // y = rint(x 2^(O8_FRAC - e))
 constexpr int O8_MAX_KD = 16384;                    // longest exact contraction per int32 accumulation (bound: 18724)
-constexpr unsigned long long O8_BIAS = 0x0080808080808080ull;
+constexpr unsigned long long O8_BIAS = 0x0000808080808080ull;
 
 __host__ __device__ inline long o8_digits_bytes(long rows, long Kd, int BR) {
   const long rpad = (rows + BR - 1) / BR * BR;

@@ -387,16 +387,25 @@ def wsyrk(K, w=None, alpha=1.0, out=None, uniform_count=None, uniform_target=0.0
     return out
 
 
-def potrf_inv(A, overwrite=False):
+POTRF_IMPL = "flow"  # "flow": one dataflow kernel (csrc/chol_flow.cu); "steps": one kernel per panel step (csrc/chol.cu)
+
+
+def potrf_inv(A, overwrite=False, impl=None):
     """Lower Cholesky factor L of A and P = L^-1.  Returns (L, P, info) with info a device int32 scalar
-    (0 = ok, else 1-based index of the first non-positive pivot)."""
+    (0 = ok, > 0: 1-based index of the first non-positive pivot, -1: dataflow wait timed out)."""
     M = A.shape[0]
     L = A if overwrite else A.clone()
     assert L.is_contiguous()
     P = torch.empty_like(L)
+    info = torch.zeros((), dtype=torch.int32, device=A.device)
+    if (impl or POTRF_IMPL) == "flow":
+        nbytes = lib().npgp_potrf_flow_workspace_bytes(M)
+        work = torch.empty(nbytes // 4 + 1, dtype=torch.int32, device=A.device)
+        check(lib().npgp_potrf_inv_flow(M, ptr(L), L.stride(0), ptr(P), P.stride(0), ptr(work), nbytes, ptr(info),
+                                        stream()), "npgp_potrf_inv_flow")
+        return L, P, info
     nbytes = lib().npgp_potrf_workspace_bytes(M)
     work = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device=A.device)
-    info = torch.zeros((), dtype=torch.int32, device=A.device)
     check(lib().npgp_potrf_inv_lower(M, ptr(L), L.stride(0), ptr(P), P.stride(0), ptr(work), nbytes, ptr(info),
                                      stream()), "npgp_potrf_inv_lower")
     return L, P, info

@@ -193,3 +193,49 @@ def test_svgp_step_with_clamped_rows_matches_dmma_path(variant):
     assert 100 < n_clamped < 500, "test problem must clamp some rows and keep some"
     assert abs(l0 - l1) < 1e-10 * abs(l0)
     assert (g0 - g1).abs().max().item() < 1e-7 * g0.abs().max().item()
+
+
+# ---- digit-level diagnostics: hand-made planes, exact integer reference ----------------------------------------------
+def encode_a_planes(D):
+    """D: (7, npad, M) int8 digits -> uint8 buffer in the A-type row layout [rb][p][ks][cj][m8][r8][k16]."""
+    _, npad, M = D.shape
+    nks = M // 32
+    t = D.view(7, npad // 128, 16, 8, nks, 2, 16)      # [p, rb, m8, r8, ks, cj, k16]
+    return t.permute(1, 0, 4, 5, 2, 3, 6).contiguous().view(torch.uint8).reshape(-1)
+
+
+def encode_b_planes(D):
+    """D: (7, Mr, Kd) int8 digits of the B operand (row blocks of 64) -> [cb][ks][p][cj][m8][r8][k16]."""
+    _, Mr, Kd = D.shape
+    nks = Kd // 32
+    t = D.view(7, Mr // 64, 8, 8, nks, 2, 16)          # [p, cb, m8, r8, ks, cj, k16]
+    return t.permute(1, 4, 0, 5, 2, 3, 6).contiguous().view(torch.uint8).reshape(-1)
+
+
+@pytest.mark.parametrize("n,M", [(128, 64), (256, 128)])
+def test_every_digit_product_is_exact(n, M):
+    """A carries only digit p, C only digit q: T must be exactly 2^(-12-8(p+q)) A_p C_q^T for the 28 kept products and 0 for
+    the dropped ones; then all digits at once against the integer sum.  Isolates a wrong product / accumulator / hazard."""
+    from nonstationary_precip_b200 import ops
+    g = torch.Generator().manual_seed(n + M)
+    DA = torch.randint(-128, 128, (7, n, M), generator=g, dtype=torch.int8)
+    DC = torch.randint(-128, 128, (7, M, M), generator=g, dtype=torch.int8)
+    ea = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ec = torch.zeros(M, dtype=torch.int32, device="cuda")
+    T = torch.empty(n, M, device="cuda")
+    bad = []
+    for p in range(7):
+        for q in range(7):
+            A1, C1 = torch.zeros_like(DA), torch.zeros_like(DC)
+            A1[p], C1[q] = DA[p], DC[q]
+            ops.o8_rowquad_digits(n, M, encode_a_planes(A1).cuda(), None, encode_b_planes(C1).cuda(), ec, T, a_expo=ea)
+            want = (DA[p].long() @ DC[q].long().T).double() * 2.0 ** (-12 - 8 * (p + q)) if p + q <= 6 else torch.zeros(n, M)
+            if not torch.equal(T.cpu(), want):
+                bad.append((p, q, (T.cpu() - want).abs().max().item() / max(want.abs().max().item(), 1e-300)))
+    assert not bad, bad
+    ops.o8_rowquad_digits(n, M, encode_a_planes(DA).cuda(), None, encode_b_planes(DC).cuda(), ec, T, a_expo=ea)
+    want = torch.zeros(n, M)
+    for p in range(7):
+        for q in range(7 - p):
+            want += (DA[p].long() @ DC[q].long().T).double() * 2.0 ** (-12 - 8 * (p + q))
+    assert ((T.cpu() - want).abs().max() / want.abs().max()).item() < 1e-15

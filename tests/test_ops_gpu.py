@@ -202,13 +202,14 @@ def test_rowquad_and_wsyrk(ops, n, M):
 
 
 # ---------------------------------------------------------------------------------------------------------------- chol
-@pytest.mark.parametrize("M", [64, 100, 300, 1024, 1536])
-def test_potrf_inv(ops, M):
+@pytest.mark.parametrize("impl", ["flow", "steps"])
+@pytest.mark.parametrize("M", [2, 64, 100, 300, 1024, 1536, 2048])
+def test_potrf_inv(ops, M, impl):
     g = torch.Generator().manual_seed(M)
     X = torch.rand(M, 3, generator=g) * 2 - 1
     ell = torch.full((3, M), 0.3)
     A = (o.gibbs_diag_K(X, X, ell, ell) + 1e-6 * torch.eye(M)).cuda()
-    L, P, info = ops.potrf_inv(A)
+    L, P, info = ops.potrf_inv(A, impl=impl)
     assert int(info) == 0
     Lw = torch.linalg.cholesky(A)
     assert rel(L, Lw) < 1e-9  # forward error ~ cond * eps
@@ -218,12 +219,37 @@ def test_potrf_inv(ops, M):
     assert torch.triu(L, 1).abs().max() == 0 and torch.triu(P, 1).abs().max() == 0
 
 
-def test_potrf_reports_first_bad_pivot(ops):
+@pytest.mark.parametrize("impl", ["flow", "steps"])
+def test_potrf_reports_first_bad_pivot(ops, impl):
     M = 200
     A = torch.eye(M, device="cuda")
     A[130, 130] = -1.0
-    _, _, info = ops.potrf_inv(A)
+    _, _, info = ops.potrf_inv(A, impl=impl)
     assert int(info) == 131
+
+
+def test_potrf_flow_two_factorisations_on_two_streams(ops):
+    """The SVGP step factors Kzz and the field prior's kernel matrix concurrently: two dataflow kernels sharing the SMs."""
+    g = torch.Generator().manual_seed(5)
+    mats = []
+    for _ in range(2):
+        X = torch.rand(1024, 3, generator=g) * 2 - 1
+        ell = torch.full((3, 1024), 0.3)
+        mats.append((o.gibbs_diag_K(X, X, ell, ell) + 1e-6 * torch.eye(1024)).cuda())
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            r1 = ops.potrf_inv(mats[0], impl="flow")
+        with torch.cuda.stream(s2):
+            r2 = ops.potrf_inv(mats[1], impl="flow")
+        outs = [r1, r2]
+    torch.cuda.synchronize()
+    for (L, P, info), A in zip(outs, mats):
+        assert int(info) == 0
+        assert rel(L @ L.T, A) < 1e-14
+        assert (P @ L - torch.eye(1024, device="cuda")).abs().max() < 1e-8
 
 
 def test_wsyrk_uniform_weight_hint(ops):
