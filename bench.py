@@ -235,13 +235,14 @@ def run_ours(args):
     launches_per_replay = 0
     if args.exec == "graph":
         c0 = lib().npgp_launch_count()
-        model.capture(Bl, world, B_GLOBAL, lr=args.lr)
+        # the NCCL all-reduce of the flat gradient and the Adam update are captured too: one graph launch per step and rank
+        model.capture(Bl, world, B_GLOBAL, lr=args.lr, all_reduce=all_reduce)
         # capture() runs the step 3 times (2 warm-ups + the captured one); the captured graph holds one step's launches
         launches_per_replay = (lib().npgp_launch_count() - c0) // 3
 
     def train(xs, ys):
         if args.exec == "graph":
-            return model.train_step_graph(xs, ys, all_reduce=all_reduce)
+            return model.train_step_graph(xs, ys)
         return model.train_step(xs, ys, lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce)
 
     def step_resident(k):
@@ -429,7 +430,15 @@ def run_ours(args):
             "roofline_kxz": {"bound": "hbm", "kernel": "gibbs_%s fwd+bwd (K written, T read: 16 B/pair)" % args.variant,
                              "achieved": kxz_gbs, "peak": hbm, "unit": "GB/s", "frac": kxz_gbs / hbm,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            # one eager single-stream step, CUDA events per section (sections overlap in the timed graph replay):
+            # replicated = work every rank repeats (O(M^3) chain on Kzz, assembly, all-reduce, Adam); sharded = work on this
+            # rank's B/G rows.  The Amdahl table in DESIGN.md is built from these.
             "sections_ms": {k: round(v, 4) for k, v in sec.items()},
+            "sections_split_ms": {
+                "replicated": round(sum(v for k, v in sec.items() if k.startswith(("zz_fwd", "m3_bwd", "assemble", "allreduce",
+                                                                                  "adam"))), 4),
+                "sharded": round(sum(v for k, v in sec.items() if not k.startswith(("zz_fwd", "m3_bwd", "assemble", "allreduce",
+                                                                                    "adam"))), 4)},
             "final_loss": final_loss,
         }
         if t_cpu is not None:

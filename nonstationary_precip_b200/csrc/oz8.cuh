@@ -106,8 +106,9 @@ __device__ __forceinline__ double o8_digits_to_double(const uint32_t (&w)[O8_NS]
   const uint32_t t1 = __byte_perm(w[4] ^ 0x80808080u, w[3] ^ 0x80808080u, sel);   // [b4, b3, ., .]
   const uint32_t lo = __byte_perm(t0, t1, 0x5410);
   const uint32_t t2 = __byte_perm(w[2] ^ 0x80808080u, w[1] ^ 0x80808080u, sel);   // [b2, b1, ., .]
-  // byte 2 = top byte, byte 3 = its sign replicated (selector nibble with bit 3 set)
-  const uint32_t hi = __byte_perm(t2, w[0], 0x0010u | ((uint32_t)(4 + c) << 8) | ((uint32_t)(8 + 4 + c) << 12));
+  // bytes 2, 3 = the sign-extended top digit (__byte_perm ignores the sign-replication bit of a selector nibble: measured)
+  const int top = (int)(signed char)(w[0] >> (8 * c));
+  const uint32_t hi = (t2 & 0xFFFFu) | ((uint32_t)top << 16);
   return __ll2double_rn((long long)((((unsigned long long)hi << 32) | lo) - O8_BIAS));
 }
 

@@ -291,7 +291,7 @@ class SVGPGibbs:
         self._join2()
         EP = o.dgemm(E, P, tri_b=1)
         C = o.dgemm(P, EP, transA=True, tri_a=2)
-        return dict(L=L, P=P, info=info, Ls=Ls, u=u, E=E, C=C)
+        return dict(L=L, P=P, info=info, Ls=Ls, u=u, E=E, EP=EP, C=C)
 
     # ------------------------------------------------------------------------------------------------------------------
     def loss_and_grad(self, xb, yb, world_size: int = 1, B_global: Optional[int] = None):
@@ -313,7 +313,7 @@ class SVGPGibbs:
         with self._sec("field_fwd"):
             fz, fx, fc = self._field_forward(xb, fz)
         self._join()
-        P, u, E, C, Ls = zz["P"], zz["u"], zz["E"], zz["C"], zz["Ls"]
+        P, u, E, EP, C, Ls = zz["P"], zz["u"], zz["E"], zz["EP"], zz["C"], zz["Ls"]
 
         # ---- data pass: K(X_B, Z) (+ mean), variance quadratic form, expected log-lik
         digits = self._digits_mode()
@@ -374,12 +374,15 @@ class SVGPGibbs:
                 wsyrk_done.record()
             with self._sec("m3_bwd+kzz_bwd"):
                 dm = o.gemv_n(P, du)
-                dE = o.dgemm(o.dgemm(P, dC, tri_a=1), P, transB=True, tri_b=2)
+                # dE = P dC P^T and E dE = (E P)(dC P^T): with W = dC P^T both follow from ONE product, so the chain to dKzz is
+                # W -> X -> P^T X -> (P^T X) P (four dependent GEMMs instead of five); dE itself only feeds the dL_s branch
+                W = o.dgemm(dC, P, transB=True, tri_b=2)
                 with self._fork2():  # dL_s branch, independent of the dKzz chain below
+                    dE = o.dgemm(P, W, tri_a=1)
                     dLs = torch.tril(o.dgemm(dE, Ls, alpha=2.0, tri_b=1))
                     g["m"].copy_(-(dm - rep * m / self.N))
                     g["Ls"].copy_(-(dLs - rep * (Ls - torch.diag(1.0 / dLs_diag)) / self.N))
-                X = o.dgemm(E, dE, alpha=2.0)
+                X = o.dgemm(EP, W, alpha=2.0)
                 X.addr_(m, dm)
                 o.phi_mask_(X, -1.0)
                 dK = o.dgemm(o.dgemm(P, X, transA=True, tri_a=2, tri_b=1), P, tri_b=1)
@@ -477,29 +480,38 @@ class SVGPGibbs:
         """loss_and_grad -> (all-reduce of the flat gradient) -> Adam.  Returns the (global) loss as a device scalar."""
         self.loss_and_grad(xb, yb, world_size, B_global)
         if all_reduce is not None:
-            all_reduce(self.grad)
-        self.adam_step(lr)
+            with self._sec("allreduce"):
+                all_reduce(self.grad)
+        with self._sec("adam"):
+            self.adam_step(lr)
         return self.grad[-2]
 
     # ---- CUDA-graph execution: the ~250 launches of a step are captured once and replayed ---------------------------
-    def capture(self, B_local: int, world_size: int = 1, B_global: Optional[int] = None, lr: float = 0.01):
-        """Capture loss_and_grad (and, single rank, the Adam update) for minibatches of B_local rows.  With several
-        ranks the NCCL all-reduce and the Adam kernel run between / after the replayed graph."""
+    def capture(self, B_local: int, world_size: int = 1, B_global: Optional[int] = None, lr: float = 0.01, all_reduce=None):
+        """Capture the whole step for minibatches of B_local rows: loss_and_grad, the all-reduce of the flat gradient
+        (`all_reduce(self.grad)`, e.g. an NCCL all-reduce -- NCCL collectives are capturable) and the Adam update, so a
+        replay is one graph launch on every rank.  Without `all_reduce` and world_size > 1 the collective and Adam run
+        after the replayed graph (train_step_graph(all_reduce=...))."""
         f64 = dict(dtype=torch.float64, device=self.dev)
         self._gx, self._gy = torch.zeros(B_local, self.d, **f64), torch.zeros(B_local, **f64)
         self._g_world, self._g_lr = world_size, lr
+        self._g_fused = world_size == 1 or all_reduce is not None
         snap = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.step_dev)]
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream (allocator pools, lazy attribute calls)
             for _ in range(2):
                 self.loss_and_grad(self._gx, self._gy, world_size, B_global)
+                if all_reduce is not None:
+                    all_reduce(self.grad)  # communicator set-up must not happen under capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self.loss_and_grad(self._gx, self._gy, world_size, B_global)
-            if world_size == 1:
+            if self._g_fused:
+                if all_reduce is not None:
+                    all_reduce(self.grad)
                 self.adam_step(lr)
         # (the graph holds raw pointers into self._i8_bufs, which live as long as the model)
         for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
@@ -511,7 +523,7 @@ class SVGPGibbs:
         self._gx.copy_(xb, non_blocking=True)
         self._gy.copy_(yb, non_blocking=True)
         self._graph.replay()
-        if self._g_world > 1:
+        if not self._g_fused:
             if all_reduce is not None:
                 all_reduce(self.grad)
             self.adam_step(self._g_lr)

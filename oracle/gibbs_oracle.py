@@ -442,7 +442,7 @@ def st_roots(x, Z, log_ell_z, hyp_t, os_s, prior_c, prior_os, prior_lam):
     return Rt, torch.sqrt(os_s) * Rs_u, Rs_u
 
 
-def st_sgpr_objective(x, y, Z, log_ell_z, hyp_t, os_s, noise, prior_c, prior_os, prior_lam):
+def st_sgpr_objective(x, y, Z, log_ell_z, hyp_t, os_s, noise, prior_c, prior_os, prior_lam, Z_prior=None):
     """ExactMarginalLogLikelihood of SparseSpatioTemporal_Nonstationary in training mode (SURVEY 3.2 applied to the sum of
     the two Nystrom kernels): [log N(y|0, R R^T + noise I) + both trace terms + log-prior] / n."""
     n = x.shape[0]
@@ -460,7 +460,9 @@ def st_sgpr_objective(x, y, Z, log_ell_z, hyp_t, os_s, noise, prior_c, prior_os,
     # the registered prior closure passes the FULL (M,3) inducing points (spatio_temporal_models.py:52-55) and the prior was
     # built with active_dims=(0,1) (experiments/spatio_temporal_exp.py:111): Kernel.__call__ selects columns 0,1 = (time, lon)
     # -- pinned by tests/golden/lognormal_prior_active_dims.npz, generated from the reference's own log_prob
-    lp = lognormal_prior_log_prob(Z[:, 0:2], log_ell_z, prior_c, prior_os, prior_lam).sum()
+    # Z_prior: the spatial kernel's (trainable) inducing points when `Z` carries the temporal kernel's frozen alias in column 0
+    Zp = Z if Z_prior is None else Z_prior
+    lp = lognormal_prior_log_prob(Zp[:, 0:2], log_ell_z, prior_c, prior_os, prior_lam).sum()
     return (ll + trace_t + trace_s + lp) / n
 
 
