@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, double
       ++k;
     }
     const int i = k + t;
+    // everything that depends on nobody happens before the first wait: the own tile of A goes to shared memory (bufC) and
+    // the mirrored, strictly upper tiles of both outputs are zeroed
+    load_tile(bufC, A, lda, i * TB, k * TB, M, i == k);
+    if (i != k) {
+      zero_tile_global(A, lda, k * TB, i * TB, M);
+      zero_tile_global(P, ldp, k * TB, i * TB, M);
+    }
     double upd[2][4][2];
     acc_zero(upd);
     for (int j = 0; j < k; ++j) {
@@ -117,33 +124,29 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, double
       mma_64<false, true>(upd, bufA, (i != k) ? bufB : bufA, p);  // L_ij L_kj^T
       __syncthreads();
     }
-    // own tile minus the accumulated update -> shared memory
-    double* dst = (i == k) ? bufC : bufA;
-    load_tile(dst, A, lda, i * TB, k * TB, M, i == k);
+    // own tile minus the accumulated update
     __syncthreads();
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int r = p.wm0 + mt * 8 + p.g, c = p.wn0 + nt * 8 + 2 * p.t4;
-        dst[r * TLD + c] -= upd[mt][nt][0];
-        dst[r * TLD + c + 1] -= upd[mt][nt][1];
+        bufC[r * TLD + c] -= upd[mt][nt][0];
+        bufC[r * TLD + c + 1] -= upd[mt][nt][1];
       }
     __syncthreads();
     if (i == k) {
       factor_invert_64(bufC, bufB, bufA, k * TB, info);
-      store_tile(bufC, A, lda, k * TB, k * TB, M);
       store_tile(bufB, P, ldp, k * TB, k * TB, M);
+      store_tile(bufC, A, lda, k * TB, k * TB, M);
     } else {
       flow_wait(&Lf[k * nb + k], abort_flag, info);
       load_tile_cg(bufB, P, ldp, k * TB, k * TB, M);
       __syncthreads();
       double acc[2][4][2];
       acc_zero(acc);
-      mma_64<false, true>(acc, bufA, bufB, p);  // L_ik = A_ik P_kk^T
+      mma_64<false, true>(acc, bufC, bufB, p);  // L_ik = A_ik P_kk^T
       acc_axpy_global(acc, A, lda, i * TB, k * TB, M, p, 1.0, false);
-      zero_tile_global(A, lda, k * TB, i * TB, M);  // mirrored (strictly upper) tiles of both outputs
-      zero_tile_global(P, ldp, k * TB, i * TB, M);
     }
     flow_signal(&Lf[i * nb + k]);
   } else {

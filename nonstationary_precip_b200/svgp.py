@@ -359,7 +359,9 @@ class SVGPGibbs:
         # Scheduling (all FP64 work shares one pipe, DFMA and DMMA alike): the SYRK runs alone at full rate on the side
         # stream; the latency-bound O(M^3) backward chain that follows it is then hidden under the FP64-bound Gibbs
         # backward on the main stream, which starts when the SYRK has finished.
-        wsyrk_done = torch.cuda.Event() if (self._side is not None and self.overlap) else None
+        # (digit path: the SYRK runs on the int8 tensor pipe and leaves the FP64 pipe, registers and ~50 KB of shared memory
+        # per SM free, so the FP64-bound Gibbs backward starts at once and runs beside it)
+        wsyrk_done = torch.cuda.Event() if (self._side is not None and self.overlap and not digits) else None
         with self._fork():
             with self._sec("wsyrk"):
                 if digits:
