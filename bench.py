@@ -451,10 +451,20 @@ def run_ours(args):
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
+    rc = 3 if (parity is not None and not parity["ok"]) else 0  # a fast step whose results differ from the reference's is not a result
     if world > 1:
-        dist.destroy_process_group()
-    if parity is not None and not parity["ok"]:
-        sys.exit(3)  # a fast step whose results differ from the reference's is not a result
+        # The captured step graph holds NCCL kernels; tearing the communicator down while that graph is alive hung
+        # (measured: the line was printed, then destroy_process_group never returned).  Drop the graph, drain the device,
+        # meet the other ranks once more and leave without the NCCL teardown.
+        model._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(rc)
+    if rc:
+        sys.exit(rc)
 
 
 def main():

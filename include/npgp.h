@@ -28,6 +28,9 @@ typedef struct CUstream_st* npgp_stream_t; /* == cudaStream_t */
 int npgp_version(void);
 /* diagnostic: kernels launched through this library so far in this process (bench.py's "gpu_launches") */
 long npgp_launch_count(void);
+/* measurement aid: buf[slot] = GPU nanosecond timer when the stream reaches this point (capturable in a CUDA graph, unlike
+ * a timing event): the real timeline of a replayed multi-stream step */
+int npgp_timestamp(long long* buf, int slot, npgp_stream_t stream);
 
 /* ---- (a) fused Gibbs cross-covariance tiles ------------------------------------------------------------------------
  * Diagonal Gibbs kernel, replaces GibbsKernel.forward (models/gibbs_kernels.py:135-162).

@@ -20,6 +20,7 @@ _d = C.c_double
 _SIGS = {
     "npgp_version": ([], _i),
     "npgp_launch_count": ([], _l),
+    "npgp_timestamp": ([_p, _i, _p], _i),
     "npgp_gibbs_diag_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p], _i),
     "npgp_gibbs_diag_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p], _i),
     "npgp_gibbs_full_fwd": ([_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _l, _p, _p, _p], _i),
@@ -121,7 +122,7 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise NpgpError("npgp kernels need CUDA tensors (got a %s tensor); there is no CPU path" % t.device.type)
-    if t.dtype not in (torch.float64, torch.int32, torch.uint8, torch.int8):
+    if t.dtype not in (torch.float64, torch.int32, torch.uint8, torch.int8, torch.int64):
         raise NpgpError("npgp kernels take fp64 data (int32 exponents / indices, uint8 digit planes); got %s" % t.dtype)
     return t.data_ptr()
 

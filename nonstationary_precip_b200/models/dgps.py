@@ -18,7 +18,7 @@ import torch
 
 from .. import functional as F
 from .. import ops
-from ..gp_base import ConstantMean, GaussianLikelihood, LinearMean, Module, RBFKernel, ScaleKernel
+from ..gp_base import ConstantMean, ExactGP, GaussianLikelihood, LinearMean, Module, MultivariateNormal, RBFKernel, ScaleKernel
 
 num_output_dims = 2
 
@@ -290,3 +290,15 @@ class DeepApproximateMLL(Module):
 
     def forward(self, output, target):
         return self.base_mll(output, target).mean(0) / sample_shard._world
+
+
+class ExactGPModel(ExactGP):
+    """The reference's plain exact-GP baseline (models/dgps.py:113-122): wiring only (out of the accelerated scope)."""
+
+    def __init__(self, train_x, train_y, likelihood, kernel):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ConstantMean()
+        self.covar_module = kernel
+
+    def forward(self, x):
+        return MultivariateNormal(self.mean_module(x), self.covar_module(x))

@@ -11,8 +11,8 @@ from __future__ import annotations
 import torch
 
 from .. import functional as F
-from ..gp_base import (ExactGP, InducingPointKernel, LowRankRootCovar, MultivariateNormal, PeriodicKernel, RBFKernel,
-                       ScaleKernel, ZeroMean, sum_covariances)
+from ..gp_base import (ExactGP, GreaterThan, InducingPointKernel, LowRankRootCovar, MultivariateNormal, PeriodicKernel,
+                       RBFKernel, ScaleKernel, ZeroMean, sum_covariances)
 from .gibbs_kernels import GibbsKernel, GibbsSafeScaleKernel, InducingGibbsKernelST
 
 
@@ -23,6 +23,24 @@ class _ScaledTemporalKernel(ScaleKernel):
         if diag and torch.equal(x1, x2):  # stationary: k(t,t) = outputscale (no n x n matrix for a diagonal)
             return self.outputscale.reshape(1).expand(x1.shape[0])
         return self.base_kernel.forward(x1, x2, outputscale=self.outputscale)
+
+
+class SpatioTemporal_Stationary(ExactGP):
+    """The reference's stationary baseline (models/spatio_temporal_models.py:17-33): wiring only, so that the driver's import
+    line resolves (experiments/spatio_temporal_exp.py:20).  Not part of the accelerated path (out of scope)."""
+
+    def __init__(self, train_x, train_y, likelihood, z=None):
+        super().__init__(train_x, train_y, likelihood)
+        self.mean_module = ZeroMean()
+        self.temporal_covar_module = ScaleKernel(RBFKernel(active_dims=(0,)) * PeriodicKernel(active_dims=(0,)),
+                                                 outputscale_constraint=GreaterThan(7), active_dims=0)
+        self.spatial_covar_module = ScaleKernel(RBFKernel(active_dims=(1, 2)), active_dims=(1, 2))
+        base = self.temporal_covar_module + self.spatial_covar_module
+        self.covar_module = base if z is None else InducingPointKernel(base_kernel=base, inducing_points=z,
+                                                                       likelihood=likelihood)
+
+    def forward(self, x):
+        return MultivariateNormal(self.mean_module(x), self.covar_module(x))
 
 
 class SparseSpatioTemporal_Nonstationary(ExactGP):

@@ -685,6 +685,11 @@ def rbf_matvec(x, z, lam, os, V, bias=None, apply_exp=False):
     return RbfMatvecFn.apply(x, z, lam, os, V, bias, apply_exp)
 
 
+def timestamp(buf, slot):
+    """buf[slot] (int64, device) = GPU nanosecond timer at this point of the current stream (graph-capturable)."""
+    check(lib().npgp_timestamp(ptr(buf), int(slot), stream()), "npgp_timestamp")
+
+
 def available() -> bool:
     import os
     return os.path.exists(_lib.LIB_PATH)

@@ -37,22 +37,31 @@ def _inv_softplus(v: float) -> float:
 
 
 class _Section:
-    """CUDA-event bracket around a named part of the step (only when model.profile is set; never under graph capture)."""
+    """Bracket around a named part of the step.  model.profile (a dict): CUDA-event pairs (eager runs only).
+    model.timeline (an int64 device buffer): GPU-timer stamps written by tiny kernels, which ARE capturable, so the real
+    start / end of every section inside a replayed multi-stream graph can be read back (SVGPGibbs.timeline_ms)."""
 
-    def __init__(self, store, name):
-        self.store, self.name = store, name
+    def __init__(self, model, name):
+        self.model, self.name = model, name
 
     def __enter__(self):
-        if self.store is not None:
+        m = self.model
+        if m.profile is not None:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
             self.a.record()
+        if m.timeline is not None:
+            self.slot = m._timeline_slots.setdefault(self.name, len(m._timeline_slots))
+            m.o.timestamp(m.timeline, 2 * self.slot)
         return self
 
     def __exit__(self, *exc):
-        if self.store is not None:
+        m = self.model
+        if m.profile is not None:
             self.b.record()
-            self.store.setdefault(self.name, []).append((self.a, self.b))
+            m.profile.setdefault(self.name, []).append((self.a, self.b))
+        if m.timeline is not None:
+            m.o.timestamp(m.timeline, 2 * self.slot + 1)
         return False
 
 
@@ -122,9 +131,19 @@ class SVGPGibbs:
         self._i8_bufs = {}  # digit planes / partial buffers of the int8 path, per local batch size (owned by this model)
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
+        self.timeline = None  # set to an int64 device buffer (>= 64 entries) to stamp section boundaries (capturable)
+        self._timeline_slots = {}
 
     def _sec(self, name):
-        return _Section(self.profile, name)
+        return _Section(self, name)
+
+    def timeline_ms(self):
+        """{section: (start_ms, end_ms)} relative to the earliest stamp of the last replayed / executed step."""
+        t = self.timeline.cpu()
+        used = [v for v in t[:2 * len(self._timeline_slots)].tolist() if v > 0]
+        t0 = min(used)
+        return {k: (round((t[2 * s].item() - t0) / 1e6, 4), round((t[2 * s + 1].item() - t0) / 1e6, 4))
+                for k, s in self._timeline_slots.items()}
 
     def section_ms(self):
         """Mean milliseconds per section from the collected events (call after torch.cuda.synchronize())."""
@@ -331,9 +350,10 @@ class SVGPGibbs:
                 T = o.o8_rowquad_digits(Bl, M, w["Ad"], s, w["Cd"], w["cexp"], w["T"], q_part=w["q_part"], gvec=gmu_early,
                                         du_part=w["du_part"])
                 du = o.o8_sum_partials(w["du_part"])
-            w["skip_count"].zero_()
-            acc, gmu, gv, _ = o.gauss_ell_parts(yb, mu, w["q_part"], s, noise, self.jitter_xx, 1e-6, 1.0 / Bg,
-                                                skip_count=w["skip_count"], skip_rows=w["skip_rows"])
+            with self._sec("gauss_ell"):
+                w["skip_count"].zero_()
+                acc, gmu, gv, _ = o.gauss_ell_parts(yb, mu, w["q_part"], s, noise, self.jitter_xx, 1e-6, 1.0 / Bg,
+                                                    skip_count=w["skip_count"], skip_rows=w["skip_rows"])
         else:
             with self._sec("kxz_fwd"):
                 K, mu = self._kernel_fwd(xb, fx, Z, fz, s, u=u)
@@ -343,6 +363,8 @@ class SVGPGibbs:
         ell = acc[0] / Bg
 
         # ---- KL and prior (replicated terms)
+        sec_kl = self._sec("kl+prior")
+        sec_kl.__enter__()
         m = p["m"]
         dLs_diag = torch.diagonal(Ls)
         kl = 0.5 * ((Ls * Ls).sum() + (m * m).sum() - M - torch.log(dLs_diag * dLs_diag).sum())
@@ -353,6 +375,7 @@ class SVGPGibbs:
                 lp = lp + (-0.5 * (r_b * fc["alpha"][b]).sum() - torch.log(fc["Ldiag"][b]).sum()
                            - 0.5 * M * LOG2PI) / M
         elbo_local = ell + rep * (-kl + lp) / self.N
+        sec_kl.__exit__()
 
         # ---- backward of the data term through K(X_B, Z)
         gv2 = 2.0 * gv
