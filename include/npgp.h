@@ -140,6 +140,16 @@ int npgp_adam_step(long n, double* p, const double* g, double* m, double* v, con
 int npgp_adam_step_dev(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
                        double beta1, double beta2, double eps, double* step_dev, double gscale, npgp_stream_t stream);
 
+/* Failure handling inside a captured step.  The reference raises from psd_safe_cholesky (models/gibbs_kernels.py:201) after
+ * its jitter ladder; a replayed CUDA graph cannot raise, so: npgp_status_update ORs bit 0 into the sticky device flag
+ * *status when *info != 0 (bad pivot / dataflow time-out) and bit 1 when *loss is not finite (either pointer may be NULL);
+ * npgp_adam_step_guarded is npgp_adam_step_dev that leaves parameters, moments and step counter untouched while
+ * *status != 0.  The host polls status every few steps and re-runs with the next jitter of the ladder. */
+int npgp_status_update(int* status, const int* info, const double* loss, npgp_stream_t stream);
+int npgp_adam_step_guarded(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
+                           double beta1, double beta2, double eps, double* step_dev, double gscale, const int* status,
+                           npgp_stream_t stream);
+
 /* ---- (d) doubly-stochastic deep GP (models/dgps.py:53-111 through GPyTorch DeepGPLayer.__call__ and
  * DeepApproximateMLL(VariationalELBO)) ----------------------------------------------------
  * Marginal reparameterised layer sample h = mu + sqrt(var) * eps over n elements.  eps_in NULL: eps ~ N(0,1) from

@@ -69,6 +69,8 @@ _SIGS = {
     "npgp_phi_mask": ([_i, _p, _l, _d, _p], _i),
     "npgp_adam_step": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _i, _d, _p], _i),
     "npgp_adam_step_dev": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _p, _d, _p], _i),
+    "npgp_status_update": ([_p, _p, _p, _p], _i),
+    "npgp_adam_step_guarded": ([_l, _p, _p, _p, _p, _p, _d, _d, _d, _d, _p, _d, _p, _p], _i),
     "npgp_rbfper_fwd": ([_i, _i, _p, _p, _p, _p, _l, _p], _i),
     "npgp_rbfper_bwd": ([_i, _i, _p, _p, _p, _p, _l, _p, _p, _p], _i),
     "npgp_dsvi_sample": ([_l, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, _p, _p, _p], _i),

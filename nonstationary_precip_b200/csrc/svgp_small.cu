@@ -114,6 +114,39 @@ __global__ void adam_dev_kernel(long n, double* __restrict__ p, const double* __
 
 __global__ void bump_step_kernel(double* step_dev) { step_dev[0] += 1.0; }
 
+// ---- failure handling inside a captured step (psd_safe_cholesky, models/gibbs_kernels.py:201, raises on a failed
+// factorisation; a replayed graph cannot raise, so the step records the failure on the device and protects the parameters)
+// status (sticky): bit 0 = a Cholesky reported a bad pivot / timed out, bit 1 = the loss is not finite
+__global__ void status_update_kernel(int* __restrict__ status, const int* __restrict__ info, const double* __restrict__ loss) {
+  int s = 0;
+  if (info && *info != 0) s |= 1;
+  if (loss && !(fabs(*loss) < 1.7e308)) s |= 2;
+  if (s) atomicOr(status, s);
+}
+
+// Adam as adam_dev_kernel, skipped entirely (parameters, moments and step counter untouched) while *status != 0
+__global__ void adam_guarded_kernel(long n, double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m,
+                                    double* __restrict__ v, const double* __restrict__ mask, double lr, double b1, double b2,
+                                    double eps, const double* __restrict__ step_dev, double gscale,
+                                    const int* __restrict__ status) {
+  if (*status != 0) return;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mask && mask[i] == 0.0) return;
+  const double t = step_dev[0] + 1.0;
+  const double bc1 = 1.0 - pow(b1, t), bc2 = 1.0 - pow(b2, t);
+  const double gi = gscale * g[i];
+  const double mi = b1 * m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * v[i] + (1.0 - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr * (mi / bc1) / (sqrt(vi / bc2) + eps);
+}
+
+__global__ void bump_step_guarded_kernel(double* step_dev, const int* __restrict__ status) {
+  if (*status == 0) step_dev[0] += 1.0;
+}
+
 // ---- deterministic variants used with the digit-plane path (no FP64 atomics) -----------------------------------------
 // mu_i = sum_s mu_part[s * stride + i] (partials of the fused K u, added in index order);  gmu_i = wscale (y_i - mu_i)/noise
 __global__ void __launch_bounds__(256) mu_gmu_parts_kernel(int n, const double* __restrict__ y,
@@ -193,6 +226,31 @@ extern "C" int npgp_adam_step_dev(long n, double* p, const double* g, double* m,
                                                                    gscale);
   NPGP_LAUNCH_CHECK();
   bump_step_kernel<<<1, 1, 0, stream>>>(step_dev);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// status (device int, sticky, zeroed by the caller once): |= 1 if *info != 0 (info may be NULL), |= 2 if *loss is not finite
+// (loss may be NULL).  Lets a captured step record a failed factorisation / a NaN objective without a host round trip.
+extern "C" int npgp_status_update(int* status, const int* info, const double* loss, cudaStream_t stream) {
+  if (!status) return NPGP_EINVAL;
+  status_update_kernel<<<1, 1, 0, stream>>>(status, info, loss);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// npgp_adam_step_dev that leaves parameters, moments and the step counter untouched while *status != 0: a failed step of a
+// replayed graph cannot corrupt the model; the host polls status and re-runs with more jitter (SVGPGibbs.recover).
+extern "C" int npgp_adam_step_guarded(long n, double* p, const double* g, double* m, double* v, const double* mask, double lr,
+                                      double beta1, double beta2, double eps, double* step_dev, double gscale,
+                                      const int* status, cudaStream_t stream) {
+  if (n < 0 || !step_dev || !status) return NPGP_EINVAL;
+  if (n == 0) return NPGP_OK;
+  if (!p || !g || !m || !v) return NPGP_EINVAL;
+  adam_guarded_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, p, g, m, v, mask, lr, beta1, beta2, eps, step_dev,
+                                                                       gscale, status);
+  NPGP_LAUNCH_CHECK();
+  bump_step_guarded_kernel<<<1, 1, 0, stream>>>(step_dev, status);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

@@ -685,6 +685,19 @@ def rbf_matvec(x, z, lam, os, V, bias=None, apply_exp=False):
     return RbfMatvecFn.apply(x, z, lam, os, V, bias, apply_exp)
 
 
+def status_update(status, info=None, loss=None):
+    """Sticky device status: |= 1 if *info != 0, |= 2 if *loss is not finite."""
+    check(lib().npgp_status_update(ptr(status), ptr(info), ptr(loss), stream()), "npgp_status_update")
+
+
+def adam_step_guarded_(p, g, m, v, step_dev, status, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, mask=None):
+    """adam_step_dev_ that does nothing while *status != 0 (failed factorisation / non-finite loss in this or an earlier step)."""
+    check(lib().npgp_adam_step_guarded(p.numel(), ptr(p), ptr(g), ptr(m), ptr(v), ptr(mask), float(lr), float(beta1),
+                                       float(beta2), float(eps), ptr(step_dev), float(gscale), ptr(status), stream()),
+          "npgp_adam_step_guarded")
+    return p
+
+
 def timestamp(buf, slot):
     """buf[slot] (int64, device) = GPU nanosecond timer at this point of the current stream (graph-capturable)."""
     check(lib().npgp_timestamp(ptr(buf), int(slot), stream()), "npgp_timestamp")

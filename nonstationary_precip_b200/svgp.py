@@ -122,6 +122,10 @@ class SVGPGibbs:
         self.eye = torch.eye(M, **f64)
         self.step_count = 0
         self.step_dev = torch.zeros(1, **f64)  # Adam step counter on the device
+        # sticky failure flag on the device (bit 0: a Cholesky failed, bit 1: non-finite loss); the guarded Adam kernel
+        # leaves the parameters alone while it is set, the host polls it (check_status) and escalates the jitter (recover)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev) if self.dev.type == "cuda" else None
+        self.extra_jitter = 0.0  # psd_safe_cholesky ladder on top of jitter_zz: 0, 1e-8, 1e-7, 1e-6 (then raise)
         self._side = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self._side2 = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self.overlap = True
@@ -231,6 +235,30 @@ class SVGPGibbs:
         else:
             self.o.gibbs_full_fwd_digits(x1, f1, x2, f2, self.kernel_jitter, scale, w["Ad"], u=u, Ku_part=w["mu_part"])
 
+    def _note(self, info=None, loss=None):
+        """Record a failed factorisation / non-finite loss in the sticky device flag (no host synchronisation)."""
+        if self.status is not None and hasattr(self.o, "status_update"):
+            self.o.status_update(self.status, info, loss)
+
+    def check_status(self) -> int:
+        """Host poll of the sticky flag (synchronises): 0 = healthy, bit 0 = Cholesky failure, bit 1 = non-finite loss."""
+        return 0 if self.status is None else int(self.status.item())
+
+    def recover(self):
+        """After a non-zero status: climb psd_safe_cholesky's jitter ladder (reference models/gibbs_kernels.py:201 through
+        GPyTorch: +1e-8, +1e-7, +1e-6 in fp64), clear the flag and drop the captured graph (the jitter is baked into it).
+        The failed steps did not touch the parameters (guarded Adam).  Raises once the ladder is exhausted."""
+        ladder = [0.0, 1e-8, 1e-7, 1e-6]
+        nxt = [j for j in ladder if j > self.extra_jitter]
+        if not nxt:
+            raise RuntimeError("Kzz not positive definite after adding jitter up to %.1e (status %d)" % (ladder[-1],
+                                                                                                      self.check_status()))
+        self.extra_jitter = nxt[0]
+        self.status.zero_()
+        regraph = self._graph is not None
+        self._graph = None
+        return regraph
+
     def _fork(self):
         """Run the enclosed launches on the side stream, ordered after everything enqueued so far."""
         if self._side is None or not self.overlap:
@@ -266,7 +294,8 @@ class SVGPGibbs:
                 lamb = self._bcast_ell(self.prior_lam[b], M)
                 Kp = o.gibbs_diag_fwd(Z, lamb, Z, lamb, self.prior_os[b:b + 1])
                 Kp.diagonal().add_(1e-4)
-                Lb, Pb, _ = o.potrf_inv(Kp, overwrite=True)
+                Lb, Pb, info_b = o.potrf_inv(Kp, overwrite=True)
+                self._note(info_b)
                 alphas.append(self._solve_spd(Pb, p["log_ell_z"][b] - self.prior_c[b]))
                 Ps.append(Pb)
                 Ldiag.append(torch.diagonal(Lb).clone())
@@ -275,7 +304,8 @@ class SVGPGibbs:
             lamr = self._bcast_ell(self.row_lam[0], M)
             Kr = o.gibbs_diag_fwd(Z, lamr, Z, lamr, self.row_os)
             Kr.diagonal().add_(1e-5)
-            _, Pr, _ = o.potrf_inv(Kr, overwrite=True)
+            _, Pr, info_r = o.potrf_inv(Kr, overwrite=True)
+            self._note(info_r)
             c.update(Pr=Pr, W=self._solve_spd(Pr, p["H"]), lamr=lamr)
         return c
 
@@ -304,8 +334,9 @@ class SVGPGibbs:
         with self._fork2():  # S - I does not depend on the factorisation: under the (latency-bound) Cholesky
             E = o.dgemm(Ls, Ls, transB=True, tri_a=1, tri_b=2) - self.eye
         Kzz = self._kernel_fwd(p["Z"], fz, p["Z"], fz, s)
-        Kzz.diagonal().add_(self.jitter_zz)
+        Kzz.diagonal().add_(self.jitter_zz + self.extra_jitter)
         L, P, info = o.potrf_inv(Kzz, overwrite=True)
+        self._note(info)
         u = o.colwsum(P, w=p["m"])  # P^T m
         self._join2()
         EP = o.dgemm(E, P, tri_b=1)
@@ -494,7 +525,13 @@ class SVGPGibbs:
     def adam_step(self, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
         self.step_count += 1
         g = self.grad[:self.theta.numel()]
-        if hasattr(self.o, "adam_step_dev_"):  # step counter on the device: identical eagerly and under graph replay
+        if self.status is not None and hasattr(self.o, "adam_step_guarded_"):
+            # the (all-reduced, hence rank-consistent) loss is checked here: a NaN on any rank stops the update on all
+            self._note(None, self.grad[-2:-1])
+            # step counter on the device (identical eagerly and under graph replay); no update while the status flag is set
+            self.o.adam_step_guarded_(self.theta, g, self.adam_m, self.adam_v, self.step_dev, self.status, lr, beta1, beta2, eps,
+                                      1.0, self.mask)
+        elif hasattr(self.o, "adam_step_dev_"):
             self.o.adam_step_dev_(self.theta, g, self.adam_m, self.adam_v, self.step_dev, lr, beta1, beta2, eps, 1.0,
                                   self.mask)
         else:

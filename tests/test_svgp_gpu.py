@@ -108,3 +108,39 @@ def test_full_size_properties(variant):
     s = torch.nn.functional.softplus(model.p["raw_outputscale"])
     assert mu.abs().max() < 1e-12
     assert (var - (s + 1e-4)).abs().max() < 1e-9
+
+
+def test_failed_cholesky_is_flagged_and_leaves_parameters_untouched():
+    """Reference behaviour: psd_safe_cholesky (models/gibbs_kernels.py:201) retries with jitter 1e-8, 1e-7, 1e-6 and then
+    raises.  A replayed graph cannot raise: the step sets a sticky device flag, the guarded Adam skips the update, the host
+    polls the flag and climbs the same ladder."""
+    from nonstationary_precip_b200.svgp import SVGPGibbs
+    x, y, Z, p, N = make_problem("diag", device="cuda", B=512, M=128, d=3, seed=3)
+    # (a) an indefinite Kzz that no jitter of the ladder repairs
+    bad = SVGPGibbs("diag", Z, N, jitter_zz=-1.0, **p)
+    before = bad.theta.clone()
+    for _ in range(2):
+        bad.train_step(x, y, lr=0.01)
+    assert bad.check_status() & 1
+    assert torch.equal(bad.theta, before) and float(bad.step_dev) == 0.0  # nothing was updated, not even to NaN
+    for _ in range(3):
+        bad.recover()
+        bad.train_step(x, y, lr=0.01)
+        assert bad.check_status() & 1
+    with pytest.raises(RuntimeError):
+        bad.recover()
+    # (b) a marginally indefinite Kzz (two coincident inducing points, pivot -1e-9): the first rung of the ladder repairs it
+    Z2 = Z.clone()
+    Z2[1] = Z2[0]
+    p2 = dict(p)
+    p2["log_ell_z"] = p["log_ell_z"].clone()
+    p2["log_ell_z"][:, 1] = p2["log_ell_z"][:, 0]
+    m = SVGPGibbs("diag", Z2, N, jitter_zz=-1e-9, learn_inducing_locations=False, **p2)
+    m.capture(512, 1, 512, lr=0.01)
+    before = m.theta.clone()
+    m.train_step_graph(x, y)
+    assert m.check_status() & 1 and torch.equal(m.theta, before)
+    assert m.recover() is True  # the graph has to be re-captured: the jitter is baked into it
+    m.capture(512, 1, 512, lr=0.01)
+    loss = m.train_step_graph(x, y)
+    assert m.check_status() == 0 and torch.isfinite(loss) and not torch.equal(m.theta, before)
