@@ -223,10 +223,17 @@ def run_ours(args):
     Z = x_h[perm[:M_IND]].to(dev)
     model = SVGPGibbs(args.variant, Z, N_TOTAL, **kw)
     model.rowquad_impl = args.gemm
+    c_engine = args.engine == "c" and args.gemm == "i8" and M_IND % 128 == 0
+    if c_engine:
+        model.use_c_engine()
     X, Y = x_h.to(dev), y_h.to(dev)  # whole data set resident in HBM (33 MB)
     Bl = B_GLOBAL // world
     nb = N_TOTAL // B_GLOBAL
-    all_reduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    torch_all_reduce = (lambda t: dist.all_reduce(t)) if world > 1 else None
+    all_reduce = torch_all_reduce
+    if c_engine and world > 1:  # the collective goes through the C ABI too (npgp_allreduce_f64 on an npgp communicator)
+        from nonstationary_precip_b200.comm import NpgpComm
+        all_reduce = NpgpComm(rank, world, dev)
 
     def rows(k):
         lo = (k % nb) * B_GLOBAL + rank * Bl
@@ -302,6 +309,8 @@ def run_ours(args):
     # ---- per-kernel evidence for the roofline (CUDA events around the sections of a few extra steps)
     model.restore(snap)
     model.overlap = False
+    if c_engine:  # the section brackets live in the Python orchestration (same kernels, same order)
+        model.engine, all_reduce_c, all_reduce = "python", all_reduce, torch_all_reduce
     for k in range(2):  # unprofiled eager steps first: the eager allocator pool (K, T: 512 MiB each) is cold after graphs
         lo, hi = rows(k)
         model.train_step(X[lo:hi], Y[lo:hi], lr=args.lr, world_size=world, B_global=B_GLOBAL, all_reduce=all_reduce)
@@ -315,6 +324,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     sec = model.section_ms()
     model.profile = None
+    if c_engine:
+        model.engine, all_reduce = "c", all_reduce_c
     out = torch.zeros(8, dtype=torch.float64, device=dev)
     peak_tf = 0.0
     for _ in range(3):
@@ -413,7 +424,9 @@ def run_ours(args):
             "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(args),  # identical in both arms
-            "impl_detail": {"exec": "cuda_graph + 3 streams" if args.exec == "graph" else "eager",
+            "impl_detail": {"engine": "npgp_svgp_step: one C-ABI call per step (forward, analytic backward, all-reduce, guarded "
+                                      "Adam)" if c_engine else "python orchestration of the C-ABI kernels (svgp.py)",
+                            "exec": "cuda_graph + 3 streams" if args.exec == "graph" else "eager",
                             "gemm": "FP64 DMMA" if args.gemm == "dmma" else
                             "FP64-exact int8 byte-digit products on tcgen05 (28 per product, int32 accumulation); "
                                     "K(X,Z) stored as 7-byte digits only"},
@@ -511,6 +524,8 @@ def main():
     ap.add_argument("--lr", type=float, default=0.01)
     ap.add_argument("--gemm", default="i8", choices=["dmma", "i8"],
                     help="row-quadratic GEMM: FP64 DMMA (dgemm.cu) or exact int8 Ozaki split on tcgen05 (ozaki.cu)")
+    ap.add_argument("--engine", default="c", choices=["c", "python"],
+                    help="c: the whole step is one C-ABI call (npgp_svgp_step); python: kernel-by-kernel orchestration in svgp.py")
     ap.add_argument("--exec", default="graph", choices=["graph", "eager"],
                     help="replay the step as a captured CUDA graph (default) or launch it eagerly")
     ap.add_argument("--ref-rows", type=int, default=16384, help="minibatch rows the CPU reference processes per step")

@@ -1,9 +1,9 @@
 /* npgp -- C ABI of the B200-native non-stationary (Gibbs) GP hot path.
  *
  * Every entry point takes raw DEVICE pointers (fp64, row-major), explicit sizes / leading dimensions and the CUDA
- * stream to run on; nothing allocates, nothing synchronises.  The only process-global state are three measurement /
- * debugging switches (npgp_set_gemm_config, npgp_o8_set_collector, npgp_rowquad_i8_debug) and the diagnostic launch
- * counter; none of them affects results.  Return value:
+ * stream to run on; nothing allocates device memory, nothing synchronises.  The only process-global state are three
+ * measurement / debugging switches (npgp_set_gemm_config, npgp_o8_set_collector, npgp_rowquad_i8_debug), the diagnostic launch
+ * counter and the lazily resolved driver / NCCL entry points; none of them affects results.  Return value:
  * 0 = ok, < 0 = argument error (NPGP_E*), > 0 = a cudaError_t from the launch.  All calls are asynchronous.
  * Outputs documented as "accumulated" are added to with atomics and must be zeroed by the caller.
  *
@@ -248,6 +248,66 @@ int npgp_gauss_ell_parts(int n, const double* y, const double* mu, const double*
                          const double* kdiag, double jitter_xx, double min_var, const double* noise, double wscale,
                          double* var_out, double* gmu, double* gv, double* acc4, int* skip_count, int* skip_rows, void* work,
                          long work_bytes, npgp_stream_t stream);
+
+/* ---- the whole SVGP-Gibbs ELBO step behind one call (csrc/svgp_step.cu) -----------------------------------------------
+ * Composition of the reference's parts as in SURVEY.md Appendix B: the inducing-point field handling of InducingGibbsKernel
+ * (models/gibbs_kernels.py:210-223) / SparseMultivariateGibbsKernel (models/sparse_multivariate_gibbs_kernel.py:67-154),
+ * GPyTorch's whitened VariationalStrategy + VariationalELBO as driven by models/dgps.py:25-35 and
+ * experiments/deepgp_spatial_bench.py:61,84-87, Adam as in experiments/spatial_exp.py:193.
+ * A plan holds the shapes, the carve-up of ONE caller-supplied workspace (npgp_svgp_workspace_bytes; 256-byte aligned), two
+ * side streams and a few events; calls on the same plan must not overlap.  Every call enqueues on `stream` (plus the plan's
+ * side streams, joined again before it returns: capturable into a CUDA graph) and returns without synchronising.
+ * theta / grad layout (doubles), n_pad = npgp_svgp_theta_size (even):
+ *   variant 1 (full-matrix Gibbs): [Z (M,d) | H (M,d) | D (d,d) | m (M) | Ls (M,M) | raw_outputscale | raw_noise]
+ *   variant 0 (diagonal Gibbs)   : [Z (M,d) | log_ell_z (d,M)   | m (M) | Ls (M,M) | raw_outputscale | raw_noise]
+ * grad has n_pad + 2 entries: grad[n_pad] = this rank's share of -ELBO, so ONE all-reduce of grad carries gradient and loss.
+ * M % 128 == 0; variant 1: d = 2 or 3; variant 0: d <= 6. */
+typedef struct {
+  int variant;           /* 0 = diagonal Gibbs kernel with a log-normal lengthscale field, 1 = full-matrix kernel, field (H, D) */
+  int d, M, B_local;     /* input dimension, inducing points, rows of this rank's share of the minibatch */
+  long N_total;          /* size of the data set (scaling of the KL / prior terms) */
+  int B_global;          /* rows of the global minibatch */
+  int world_size;        /* ranks: the replicated KL / prior terms are weighted 1 / world_size on every rank */
+  double jitter_zz, jitter_xx, kernel_jitter, min_var; /* GPyTorch's 1e-6 / 1e-4, the reference's 1e-5, variance floor 1e-6 */
+  double extra_jitter;   /* psd_safe_cholesky ladder on top of jitter_zz (npgp_svgp_set_extra_jitter) */
+  int learn_z, include_prior;
+  const double* row_os;  /* variant 1: device scalar, outputscale of the row kernel of the matrix-normal field prior */
+  const double* row_lam; /* variant 1: (d) its lengthscales */
+  const double* prior_c; /* variant 0: (d) prior means of log ell, */
+  const double* prior_os;  /*          (d) prior outputscales, */
+  const double* prior_lam; /*          (d,d) prior lengthscales, one row per output dimension */
+  long long* timeline;   /* optional: 2 * npgp_svgp_num_sections() GPU-timer stamps (start, end per section); NULL = off */
+} npgp_svgp_config;
+typedef struct npgp_svgp_plan npgp_svgp_plan;
+long npgp_svgp_theta_size(const npgp_svgp_config* cfg);
+long npgp_svgp_workspace_bytes(const npgp_svgp_config* cfg);
+int npgp_svgp_plan_create(npgp_svgp_plan** plan, const npgp_svgp_config* cfg, void* workspace, long workspace_bytes);
+int npgp_svgp_plan_destroy(npgp_svgp_plan* plan);
+int npgp_svgp_set_extra_jitter(npgp_svgp_plan* plan, double extra);
+int npgp_svgp_num_sections(void);
+const char* npgp_svgp_section_name(int i);
+/* x (B_local,d), y (B_local).  fwd: everything up to the loss (grad[n_pad] = this rank's share of -ELBO); K(X_B,Z) (digit
+ * planes), T = K C, the gradient seeds and the Z-side factors stay in the workspace.  status (optional, device, sticky): bit 0
+ * is set when a Cholesky fails.  bwd: grad[0 .. n_pad) of the forward that ran last on this plan (same x, theta). */
+int npgp_svgp_elbo_fwd(npgp_svgp_plan* plan, const double* x, const double* y, const double* theta, double* grad, int* status,
+                       npgp_stream_t stream);
+int npgp_svgp_elbo_bwd(npgp_svgp_plan* plan, const double* x, const double* theta, double* grad, npgp_stream_t stream);
+/* fwd + bwd + all-reduce of grad (comm: npgp_comm_create handle, NULL = single rank) + npgp_status_update on the reduced loss
+ * + npgp_adam_step_guarded on theta */
+int npgp_svgp_step(npgp_svgp_plan* plan, const double* x, const double* y, double* theta, double* grad, double* adam_m,
+                   double* adam_v, const double* mask, double* step_dev, int* status, double lr, double beta1, double beta2,
+                   double eps, void* comm, npgp_stream_t stream);
+/* device pointers into the workspace (inspection): 0 mu (B), 1 T (B,M), 2 P (M,M), 3 C (M,M), 4 u (M), 5 g_mu (B), 6 g_v (B),
+ * 7 acc4, 8 info (ints: Kzz, then the prior-kernel factorisations) */
+const void* npgp_svgp_buffer(npgp_svgp_plan* plan, int which);
+
+/* ---- the path's one collective (csrc/comm.cu): sum all-reduce of the flat fp64 gradient buffer.
+ * NCCL is bound at run time (dlopen), the communicator is an opaque handle.  id128: 128-byte token made on one rank by
+ * npgp_comm_unique_id and shipped to the others by any means; npgp_comm_create is collective and binds to the current device. */
+int npgp_comm_unique_id(void* id128);
+int npgp_comm_create(void** comm, const void* id128, int nranks, int rank);
+int npgp_comm_destroy(void* comm);
+int npgp_allreduce_f64(void* comm, double* buf, long n, npgp_stream_t stream);
 
 /* ---- measurement helpers (csrc/peak.cu): FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop) and the int8
  * tensor-core ceiling (blocks x reps x 8 back-to-back tcgen05.mma kind::i8 of 128 x n_tile x 32 from resident shared

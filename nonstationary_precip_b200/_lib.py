@@ -17,6 +17,17 @@ _i = C.c_int
 _l = C.c_long
 _d = C.c_double
 
+
+
+class SvgpConfig(C.Structure):
+    """npgp_svgp_config of include/npgp.h (field for field)."""
+    _fields_ = [("variant", C.c_int), ("d", C.c_int), ("M", C.c_int), ("B_local", C.c_int), ("N_total", C.c_long),
+                ("B_global", C.c_int), ("world_size", C.c_int), ("jitter_zz", C.c_double), ("jitter_xx", C.c_double),
+                ("kernel_jitter", C.c_double), ("min_var", C.c_double), ("extra_jitter", C.c_double), ("learn_z", C.c_int),
+                ("include_prior", C.c_int), ("row_os", C.c_void_p), ("row_lam", C.c_void_p), ("prior_c", C.c_void_p),
+                ("prior_os", C.c_void_p), ("prior_lam", C.c_void_p), ("timeline", C.c_void_p)]
+
+
 _SIGS = {
     "npgp_version": ([], _i),
     "npgp_launch_count": ([], _l),
@@ -76,6 +87,21 @@ _SIGS = {
     "npgp_dsvi_sample": ([_l, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, _p, _p, _p], _i),
     "npgp_dsvi_sample_bwd": ([_l, _p, _p, _p, _p, _p, _p], _i),
     "npgp_gauss_ell_batched": ([_i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p, _p], _i),
+    "npgp_svgp_theta_size": ([_p], _l),
+    "npgp_svgp_workspace_bytes": ([_p], _l),
+    "npgp_svgp_plan_create": ([_p, _p, _p, _l], _i),
+    "npgp_svgp_plan_destroy": ([_p], _i),
+    "npgp_svgp_set_extra_jitter": ([_p, _d], _i),
+    "npgp_svgp_num_sections": ([], _i),
+    "npgp_svgp_section_name": ([_i], C.c_char_p),
+    "npgp_svgp_elbo_fwd": ([_p, _p, _p, _p, _p, _p, _p], _i),
+    "npgp_svgp_elbo_bwd": ([_p, _p, _p, _p, _p], _i),
+    "npgp_svgp_step": ([_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _d, _d, _d, _d, _p, _p], _i),
+    "npgp_svgp_buffer": ([_p, _i], _p),
+    "npgp_comm_unique_id": ([_p], _i),
+    "npgp_comm_create": ([_p, _p, _i, _i], _i),
+    "npgp_comm_destroy": ([_p], _i),
+    "npgp_allreduce_f64": ([_p, _p, _l, _p], _i),
 }
 
 _lib = None

@@ -15,7 +15,8 @@
 // operands, or directly by the Gibbs tile kernels (gibbs_digits.cu) for K(X,Z), which then never exists in FP64.  Warp
 // roles per CTA (one persistent CTA per SM): warp 0 producer (cp.async.bulk / TMA tensor copies global -> shared, mbarrier
 // completion), warp 1 MMA issuer (one elected lane, 28 MMAs per 32-byte k-step, A-operand collector reuse across the B
-// digits, tcgen05.commit frees the stage), warps 2-5 epilogue (tcgen05.ld, integer recombination, power-of-two scaling,
+// digits, tcgen05.commit frees the stage), epilogue warps (4 in the SYRK, 8 in the row-quadratic kernel, which releases TMEM
+// as soon as the accumulators sit in registers: tcgen05.ld, integer recombination, power-of-two scaling,
 // fused row dot / column sums against the K tile rebuilt from the digits while the MMAs run).
 // The SYRK contracts over the ROWS of K.  With a matrix-wide scale it reads the same row-layout planes MN-major
 // (instruction descriptor a_major = b_major = 1; verified by tools/probes/umma_i8_probe2.cu), each operand tile fetched by
@@ -32,7 +33,8 @@
 
 namespace npgp {
 
-constexpr int O8_THREADS = 192;
+constexpr int O8_THREADS = 192;             // SYRK: producer, MMA issuer, 4 epilogue warps
+constexpr int O8_RQ_THREADS = 320;          // row-quadratic kernel: producer, MMA issuer, 8 epilogue warps
 constexpr int O8_RQ_STAGES = 3;
 constexpr int O8_SY_STAGES = 4;
 constexpr int O8_KLD = O8_BN + 2;            // leading dimension (doubles) of the staged K tile
@@ -271,7 +273,7 @@ __device__ __forceinline__ double o8_scale_or_nan(int e, int shift) {
 //   q:       q_stride == 0: q[row] += (atomics);  q_stride > 0: q[cb * q_stride + row] = partial (deterministic)
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool COLL>
-__global__ void __launch_bounds__(O8_THREADS, 1)
+__global__ void __launch_bounds__(O8_RQ_THREADS, 1)
 o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int* __restrict__ ea,
                   const double* __restrict__ a_scale, const int8_t* __restrict__ Bs, const int* __restrict__ eb,
                   const double* __restrict__ Kmat, long ldk, double* __restrict__ T, long ldt, double* __restrict__ q,
@@ -280,7 +282,7 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
   uint8_t* sA = o8_sm;
   uint8_t* sB = o8_sm + O8_RQ_STAGES * O8_A_STAGE;
   double* sK = reinterpret_cast<double*>(o8_sm + O8_RQ_STAGES * (O8_A_STAGE + O8_B_STAGE));  // 128 x O8_KLD tile of K
-  __shared__ double scol[O8_BN], sg[O8_BM];
+  __shared__ double scol[O8_BN], sg[O8_BM], sq[O8_BM];
   __shared__ __align__(8) uint64_t full[O8_RQ_STAGES], empty[O8_RQ_STAGES], acc_full, acc_empty;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,7 +295,7 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       o8_mbar_init(&empty[s], 1);
     }
     o8_mbar_init(&acc_full, 1);
-    o8_mbar_init(&acc_empty, 4);  // one arrival per epilogue warp
+    o8_mbar_init(&acc_empty, 8);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -367,9 +369,12 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       dbg[3] = clock64() - t_all;
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3, et = tid - 64;  // et: 0..127
-    const int rloc = quad * 32 + lane;         // this thread's row inside the tile (= its TMEM lane)
+    // ===== epilogue: warps 2..9.  TMEM lane quadrant = warp % 4 (hardware rule), column half = (warp - 2) / 4: a thread owns
+    // 32 columns of one row.  Phase 1 (the only part the MMA issuer waits for): TMEM -> registers, recombined to one double per
+    // entry, then the accumulators are released; phase 2 (scaling, T stores, row dot) runs under the next tile's MMAs. =====
+    const int quad = warp & 3, half = (warp - 2) >> 2, et = tid - 64;  // et: 0..255
+    const int rloc = quad * 32 + lane;                                 // this thread's row inside the tile (= its TMEM lane)
+    constexpr int HC = O8_BN / 2;                                      // columns per thread
     const bool need_k = (q != nullptr) || (du_part != nullptr);
     const int e_all = ea ? 0 : o8_exponent_of_scale(*a_scale);
     uint32_t acc_phase = 0;
@@ -381,23 +386,23 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       // while the MMAs of this tile run: the K tile (row dot, column sums) and the column scales
       if (need_k) {
         if (Kmat) {
-          for (int rr = et >> 5; rr < O8_BM; rr += 4) {  // one row (512 contiguous bytes) per warp instruction
+          for (int rr = et >> 5; rr < O8_BM; rr += 8) {  // one row (512 contiguous bytes) per warp instruction
             const int gr = rb * O8_BM + rr;
             double2 d = make_double2(0.0, 0.0);
             if (gr < n) d = *reinterpret_cast<const double2*>(Kmat + (long)gr * ldk + cb * O8_BN + 2 * lane);
             *reinterpret_cast<double2*>(sK + rr * O8_KLD + 2 * lane) = d;
           }
         } else {
-          // rebuild the thread's row of the tile from the digit planes (the two k-steps that hold these 64 columns)
+          // rebuild the thread's 32 columns from the digit planes (= one k-step of the A block: two 16-byte halves)
           const double asc = (er == O8_POISON) ? __longlong_as_double(0x7FF8000000000000ll) : o8_pow2(er - O8_FRAC);
-          const int8_t* ab = As + o8_a_offset((long)rb * O8_BM + rloc, cb * O8_BN, nks);
+          const int8_t* ab = As + o8_a_offset((long)rb * O8_BM + rloc, cb * O8_BN + half * HC, nks);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {  // (k-step, 16-column half)
+          for (int h = 0; h < 2; ++h) {  // 16-column half of the k-step
             uint4 dg[O8_NS];
 #pragma unroll
             for (int p = 0; p < O8_NS; ++p)
-              dg[p] = *reinterpret_cast<const uint4*>(ab + ((long)p * nks + (h >> 1)) * O8_A_PLANE + (h & 1) * (O8_BM * 16));
-            double* dst = sK + rloc * O8_KLD + h * 16;
+              dg[p] = *reinterpret_cast<const uint4*>(ab + (long)p * nks * O8_A_PLANE + h * (O8_BM * 16));
+            double* dst = sK + rloc * O8_KLD + half * HC + h * 16;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               uint32_t w[O8_NS];
@@ -412,8 +417,8 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
         }
       }
       if (et < O8_BN) scol[et] = o8_scale_or_nan(eb[cb * O8_BN + et], 0);
-      if (du_part) sg[rloc] = (row < n) ? gvec[row] : 0.0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (du_part && half == 0) sg[rloc] = (row < n) ? gvec[row] : 0.0;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (du_part && et < O8_BN) {
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll 8
@@ -427,41 +432,45 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
       o8_mbar_wait(&acc_full, acc_phase);
       if (dbg) w_accfull += clock64() - c0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double rs = o8_scale_or_nan(er, -36);  // 2^(e_i - 12 - 24)
-      const double* krow = sK + rloc * O8_KLD;
-      double qsum = 0.0;
-      for (int c0i = 0; c0i < O8_BN; c0i += 8) {
+      // ---- phase 1: 7 x 32 accumulator columns of this row -> 32 doubles (exact integers, unscaled)
+      double val[HC];
+#pragma unroll
+      for (int c0i = 0; c0i < HC; c0i += 8) {
         uint32_t g[O8_NS][8];
 #pragma unroll
         for (int t = 0; t < O8_NS; ++t)
-          o8_tmem_ld8(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * O8_BN + c0i), g[t]);
+          o8_tmem_ld8(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * O8_BN + half * HC + c0i), g[t]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        double out[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] = o8_recombine(g, j) * rs * scol[c0i + j];
-        if (row < n) {
-          double* tp = T + (long)row * ldt + cb * O8_BN + c0i;
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(tp + j) = make_double2(out[j], out[j + 1]);
-          if (q) {
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const double2 kk = *reinterpret_cast<const double2*>(krow + c0i + j);
-              qsum = fma(out[j], kk.x, qsum);
-              qsum = fma(out[j + 1], kk.y, qsum);
-            }
-          }
-        }
-      }
-      if (q && row < n) {
-        if (q_stride > 0) q[(long)cb * q_stride + row] = qsum;
-        else atomicAdd(&q[row], qsum);
+        for (int j = 0; j < 8; ++j) val[c0i + j] = o8_recombine(g, j);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) o8_mbar_arrive(&acc_empty);
+      if (lane == 0) o8_mbar_arrive(&acc_empty);  // the next tile's MMAs may overwrite TMEM from here on
       acc_phase ^= 1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with sK / scol / sg before the next tile overwrites them
+      // ---- phase 2
+      const double rs = o8_scale_or_nan(er, -36);  // 2^(e_i - 12 - 24)
+      const double* krow = sK + rloc * O8_KLD + half * HC;
+      const double* sc = scol + half * HC;
+      double qsum = 0.0;
+      if (row < n) {
+        double* tp = T + (long)row * ldt + cb * O8_BN + half * HC;
+#pragma unroll
+        for (int j = 0; j < HC; j += 2) {
+          const double o0 = val[j] * rs * sc[j], o1 = val[j + 1] * rs * sc[j + 1];
+          *reinterpret_cast<double2*>(tp + j) = make_double2(o0, o1);
+          if (q) {
+            const double2 kk = *reinterpret_cast<const double2*>(krow + j);
+            qsum = fma(o0, kk.x, qsum);
+            qsum = fma(o1, kk.y, qsum);
+          }
+        }
+      }
+      if (q && q_stride == 0 && row < n) atomicAdd(&q[row], qsum);
+      if (q && q_stride > 0 && half == 1) sq[rloc] = qsum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with sK / scol / sg before the next tile overwrites them
+      // (sq is rewritten only after the next tile's first barrier, which these readers pass first)
+      if (q && q_stride > 0 && half == 0 && row < n) q[(long)cb * q_stride + row] = qsum + sq[rloc];
     }
     if (dbg && blockIdx.x == 0 && warp == 2 && lane == 0) dbg[4] = w_accfull;
   }
@@ -677,21 +686,33 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int n_chunks
   }
 }
 
-// out[j] = sum_b part[b * N + j] in index order (column sums of the row-quadratic kernel's per-row-block partials)
+// out[j] = sum_b part[b * N + j] in a fixed order (column sums of the row-quadratic kernel's per-row-block partials).
+// CTA = 32 columns x 8 row groups: thread (g, c) adds rows g, g + 8, ... (four independent chains), the eight groups are
+// combined in index order through shared memory -- bitwise reproducible, and 32x more CTAs than one thread per column.
 __global__ void __launch_bounds__(256) o8_sum_partials_kernel(int nb, int N, const double* __restrict__ part,
                                                               double* __restrict__ out) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= N) return;
+  __shared__ double sm[8][33];
+  const int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + c;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int b = 0;
-  for (; b + 3 < nb; b += 4) {
-    a0 += part[(long)b * N + j];
-    a1 += part[(long)(b + 1) * N + j];
-    a2 += part[(long)(b + 2) * N + j];
-    a3 += part[(long)(b + 3) * N + j];
+  if (j < N) {
+    int b = g;
+    for (; b + 24 < nb; b += 32) {
+      a0 += part[(long)b * N + j];
+      a1 += part[(long)(b + 8) * N + j];
+      a2 += part[(long)(b + 16) * N + j];
+      a3 += part[(long)(b + 24) * N + j];
+    }
+    for (; b < nb; b += 8) a0 += part[(long)b * N + j];
   }
-  for (; b < nb; ++b) a0 += part[(long)b * N + j];
-  out[j] = (a0 + a1) + (a2 + a3);
+  sm[g][c] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (g == 0 && j < N) {
+    double t = sm[0][c];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][c];
+    out[j] = t;
+  }
 }
 
 static int o8_syrk_chunks(int nks, int n_tiles, int* spc_out) {
@@ -781,11 +802,11 @@ extern "C" int npgp_o8_rowquad_digits(int n, int M, const void* a_digits, const 
   const int tiles = (int)(npad / O8_BM) * (M / O8_BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   if (g_o8_collector)
-    o8_rowquad_kernel<true><<<grid, O8_THREADS, O8_RQ_SMEM, stream>>>(n, M, M, (const int8_t*)a_digits, a_expo, a_scale,
+    o8_rowquad_kernel<true><<<grid, O8_RQ_THREADS, O8_RQ_SMEM, stream>>>(n, M, M, (const int8_t*)a_digits, a_expo, a_scale,
                                                                      (const int8_t*)c_digits, c_expo, Kmat, ldk, T, ldt, q,
                                                                      q_stride, gvec, du_part, g_o8_dbg);
   else
-    o8_rowquad_kernel<false><<<grid, O8_THREADS, O8_RQ_SMEM, stream>>>(n, M, M, (const int8_t*)a_digits, a_expo, a_scale,
+    o8_rowquad_kernel<false><<<grid, O8_RQ_THREADS, O8_RQ_SMEM, stream>>>(n, M, M, (const int8_t*)a_digits, a_expo, a_scale,
                                                                       (const int8_t*)c_digits, c_expo, Kmat, ldk, T, ldt, q,
                                                                       q_stride, gvec, du_part, g_o8_dbg);
   NPGP_LAUNCH_CHECK();
@@ -797,7 +818,7 @@ extern "C" int npgp_o8_sum_partials(int nb, int N, const double* part, double* o
   if (nb < 0 || N < 0) return NPGP_EINVAL;
   if (N == 0) return NPGP_OK;
   if (!part || !out) return NPGP_EINVAL;
-  o8_sum_partials_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(nb, N, part, out);
+  o8_sum_partials_kernel<<<ceil_div(N, 32), 256, 0, stream>>>(nb, N, part, out);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

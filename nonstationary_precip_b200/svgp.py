@@ -133,6 +133,10 @@ class SVGPGibbs:
         # ozaki.cu; needs M % 64 == 0).  Same result to FP64 rounding (tests/test_ozaki_gpu.py).
         self.rowquad_impl = "i8"  # falls back to "dmma" per call when M is not a multiple of 128
         self._i8_bufs = {}  # digit planes / partial buffers of the int8 path, per local batch size (owned by this model)
+        # "python": the step is orchestrated below, kernel by kernel through `ops`; "c": ONE C call per pass (csrc/svgp_step.cu:
+        # npgp_svgp_elbo_fwd / _bwd / npgp_svgp_step on a plan with its own workspace and side streams; digit path only)
+        self.engine = "python"
+        self._plans = {}
         self._graph = None
         self.profile = None  # set to a dict to collect per-section CUDA-event pairs
         self.timeline = None  # set to an int64 device buffer (>= 64 entries) to stamp section boundaries (capturable)
@@ -147,7 +151,7 @@ class SVGPGibbs:
         used = [v for v in t[:2 * len(self._timeline_slots)].tolist() if v > 0]
         t0 = min(used)
         return {k: (round((t[2 * s].item() - t0) / 1e6, 4), round((t[2 * s + 1].item() - t0) / 1e6, 4))
-                for k, s in self._timeline_slots.items()}
+                for k, s in self._timeline_slots.items() if t[2 * s].item() > 0 and t[2 * s + 1].item() > 0}
 
     def section_ms(self):
         """Mean milliseconds per section from the collected events (call after torch.cuda.synchronize())."""
@@ -343,10 +347,74 @@ class SVGPGibbs:
         C = o.dgemm(P, EP, transA=True, tri_a=2)
         return dict(L=L, P=P, info=info, Ls=Ls, u=u, E=E, EP=EP, C=C)
 
+    # ---- C engine ---------------------------------------------------------------------------------------------------
+    def use_c_engine(self, on: bool = True):
+        """Route loss_and_grad / train_step through the C-ABI step (needs M % 128 == 0: the digit-plane path)."""
+        if on and self.M % 128:
+            raise ValueError("the C step needs M % 128 == 0 (got %d)" % self.M)
+        self.engine = "c" if on else "python"
+        return self
+
+    def _plan(self, Bl, world_size, Bg):
+        """npgp_svgp_plan for this batch shape (created on first use: before graph capture, capture() warms up first)."""
+        from ._lib import SvgpConfig, check, lib, ptr
+        import ctypes as C
+        tl = self.timeline.data_ptr() if self.timeline is not None else None
+        key = (Bl, world_size, Bg, self.learn_z, self.include_prior, tl)
+        ent = self._plans.get(key)
+        if ent is not None and ent["extra"] != self.extra_jitter:  # psd_safe_cholesky ladder (recover())
+            check(lib().npgp_svgp_set_extra_jitter(ent["handle"], float(self.extra_jitter)), "npgp_svgp_set_extra_jitter")
+            ent["extra"] = self.extra_jitter
+        if ent is None:
+            full = self.variant == "full"
+            cfg = SvgpConfig(variant=1 if full else 0, d=self.d, M=self.M, B_local=Bl, N_total=self.N, B_global=Bg,
+                             world_size=world_size, jitter_zz=self.jitter_zz, jitter_xx=self.jitter_xx,
+                             kernel_jitter=self.kernel_jitter, min_var=1e-6, extra_jitter=self.extra_jitter,
+                             learn_z=int(self.learn_z), include_prior=int(self.include_prior),
+                             row_os=ptr(self.row_os) if full else None, row_lam=ptr(self.row_lam) if full else None,
+                             prior_c=None if full else ptr(self.prior_c), prior_os=None if full else ptr(self.prior_os),
+                             prior_lam=None if full else ptr(self.prior_lam), timeline=tl)
+            assert lib().npgp_svgp_theta_size(C.byref(cfg)) == self.theta.numel()
+            nbytes = lib().npgp_svgp_workspace_bytes(C.byref(cfg))
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.dev)
+            off = (-ws.data_ptr()) % 256
+            handle = C.c_void_p()
+            check(lib().npgp_svgp_plan_create(C.byref(handle), C.byref(cfg), ws.data_ptr() + off, nbytes), "npgp_svgp_plan_create")
+            ent = self._plans[key] = dict(handle=handle, ws=ws, cfg=cfg, extra=self.extra_jitter)
+            if tl is not None:  # the C step stamps its sections into fixed slots
+                self._timeline_slots = {name: i for i, name in enumerate(self.c_section_names())}
+        return ent
+
+    def _plan_view(self, ent, which, count, dtype=torch.float64):
+        """Torch view of one of the plan's workspace buffers (npgp_svgp_buffer)."""
+        from ._lib import lib
+        addr = lib().npgp_svgp_buffer(ent["handle"], which)
+        off = addr - ent["ws"].data_ptr()
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return ent["ws"][off:off + nbytes].view(dtype)
+
+    def _c_loss_and_grad(self, xb, yb, world_size, B_global):
+        from ._lib import check, lib, ptr, stream
+        Bl = xb.shape[0]
+        Bg = B_global if B_global is not None else Bl * world_size
+        ent = self._plan(Bl, world_size, Bg)
+        xb, yb = xb.contiguous(), yb.contiguous()
+        check(lib().npgp_svgp_elbo_fwd(ent["handle"], ptr(xb), ptr(yb), ptr(self.theta), ptr(self.grad), ptr(self.status),
+                                       stream()), "npgp_svgp_elbo_fwd")
+        check(lib().npgp_svgp_elbo_bwd(ent["handle"], ptr(xb), ptr(self.theta), ptr(self.grad), stream()), "npgp_svgp_elbo_bwd")
+        self.last = dict(info=self._plan_view(ent, 8, 1, torch.int32)[0], mu=self._plan_view(ent, 0, Bl))
+        return self.grad[-2]
+
+    def c_section_names(self):
+        from ._lib import lib
+        return [lib().npgp_svgp_section_name(i).decode() for i in range(lib().npgp_svgp_num_sections())]
+
     # ------------------------------------------------------------------------------------------------------------------
     def loss_and_grad(self, xb, yb, world_size: int = 1, B_global: Optional[int] = None):
         """Fills self.grad with d(-ELBO)/d(theta) for this rank's rows and returns this rank's share of -ELBO
         (also stored in self.grad[-2]); summing over ranks (one all-reduce of self.grad) gives the global values."""
+        if self.engine == "c":
+            return self._c_loss_and_grad(xb, yb, world_size, B_global)
         o, p, g, M, d = self.o, self.p, self.g, self.M, self.d
         Z = p["Z"]
         Bl = xb.shape[0]
@@ -540,6 +608,19 @@ class SVGPGibbs:
 
     def train_step(self, xb, yb, lr=0.01, world_size=1, B_global=None, all_reduce=None):
         """loss_and_grad -> (all-reduce of the flat gradient) -> Adam.  Returns the (global) loss as a device scalar."""
+        from .comm import NpgpComm
+        if self.engine == "c" and (isinstance(all_reduce, NpgpComm) or (all_reduce is None and world_size == 1)):
+            # the whole step is ONE C call (npgp_svgp_step): forward, backward, all-reduce on the npgp communicator, guarded Adam
+            from ._lib import check, lib, ptr, stream
+            Bl = xb.shape[0]
+            ent = self._plan(Bl, world_size, B_global if B_global is not None else Bl * world_size)
+            xb, yb = xb.contiguous(), yb.contiguous()
+            check(lib().npgp_svgp_step(ent["handle"], ptr(xb), ptr(yb), ptr(self.theta), ptr(self.grad), ptr(self.adam_m),
+                                       ptr(self.adam_v), ptr(self.mask), ptr(self.step_dev), ptr(self.status), float(lr), 0.9,
+                                       0.999, 1e-8, all_reduce.handle if all_reduce is not None else None, stream()),
+                  "npgp_svgp_step")
+            self.step_count += 1
+            return self.grad[-2]
         self.loss_and_grad(xb, yb, world_size, B_global)
         if all_reduce is not None:
             with self._sec("allreduce"):
@@ -561,8 +642,12 @@ class SVGPGibbs:
         snap = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.step_dev)]
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
+        c_fused = self.engine == "c" and self._g_fused
         with torch.cuda.stream(side):  # warm-up off the default stream (allocator pools, lazy attribute calls)
             for _ in range(2):
+                if c_fused:
+                    self.train_step(self._gx, self._gy, lr, world_size, B_global, all_reduce)
+                    continue
                 self.loss_and_grad(self._gx, self._gy, world_size, B_global)
                 if all_reduce is not None:
                     all_reduce(self.grad)  # communicator set-up must not happen under capture
@@ -570,11 +655,14 @@ class SVGPGibbs:
         torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self.loss_and_grad(self._gx, self._gy, world_size, B_global)
-            if self._g_fused:
-                if all_reduce is not None:
-                    all_reduce(self.grad)
-                self.adam_step(lr)
+            if c_fused:
+                self.train_step(self._gx, self._gy, lr, world_size, B_global, all_reduce)
+            else:
+                self.loss_and_grad(self._gx, self._gy, world_size, B_global)
+                if self._g_fused:
+                    if all_reduce is not None:
+                        all_reduce(self.grad)
+                    self.adam_step(lr)
         # (the graph holds raw pointers into self._i8_bufs, which live as long as the model)
         for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
             t.copy_(s)

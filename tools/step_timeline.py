@@ -19,12 +19,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ranks", type=int, default=1)
 ap.add_argument("--variant", default="full")
 ap.add_argument("--replays", type=int, default=10)
+ap.add_argument("--engine", default="c", choices=["c", "python"])
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 x_h, y_h, perm = bench.make_data(bench.N_TOTAL, bench.DIM)
 kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.make_params(args.variant, bench.M_IND, bench.DIM).items()}
 model = SVGPGibbs(args.variant, x_h[perm[:bench.M_IND]].to(dev), bench.N_TOTAL, **kw)
 Bl = bench.B_GLOBAL // args.ranks
+if args.engine == "c":
+    model.use_c_engine()
 model.timeline = torch.zeros(128, dtype=torch.int64, device=dev)
 model.capture(Bl, args.ranks, bench.B_GLOBAL, lr=0.01)
 X, Y = x_h[:Bl].to(dev), y_h[:Bl].to(dev)
@@ -38,7 +41,7 @@ for _ in range(args.replays):
 ev1.record()
 torch.cuda.synchronize()
 tl = model.timeline_ms()
-out = {"ranks": args.ranks, "B_local": Bl, "ms_per_step": round(ev0.elapsed_time(ev1) / args.replays, 4),
+out = {"engine": args.engine, "ranks": args.ranks, "B_local": Bl, "ms_per_step": round(ev0.elapsed_time(ev1) / args.replays, 4),
        "timeline_ms(start,end)": dict(sorted(tl.items(), key=lambda kv: kv[1][0]))}
 print(json.dumps(out))
 for k, (a, b) in sorted(tl.items(), key=lambda kv: kv[1][0]):
