@@ -38,7 +38,7 @@ constexpr int O8_RQ_THREADS = 320;          // row-quadratic kernel: producer, M
 constexpr int O8_RQ_STAGES = 3;
 constexpr int O8_SY_STAGES = 4;
 constexpr int O8_KLD = O8_BN + 2;            // leading dimension (doubles) of the staged K tile
-constexpr int O8_CHUNK_STAGES = 256;         // <= 8192 contraction rows per int32 accumulation of the SYRK
+constexpr int O8_MAX_SEG = 512;              // <= 16384 contraction rows per int32 accumulation of the SYRK (bound: 18724)
 constexpr int O8_RQ_SMEM = O8_RQ_STAGES * (O8_A_STAGE + O8_B_STAGE) + O8_BM * O8_KLD * 8 + 1024;
 constexpr int O8_SY_SMEM = O8_SY_STAGES * (O8_A_STAGE + O8_B_STAGE) + 1024;
 
@@ -480,6 +480,64 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Work decomposition of the SYRK.  Items = (row chunk, tile), chunk-major, a chunk being <= O8_MAX_SEG k-stages (int32
+// exactness) -- CTAs that run at the same time work on the same rows of X, which therefore come from L2 (a first version
+// that gave every CTA one contiguous range of the (tile, stage) space was DRAM bound: 6 GB of traffic instead of 0.56).
+// Full waves of items go one item per CTA; the items of the last, partial wave ("stream-K" remainder) are cut into equal
+// contiguous stage ranges so that all CTAs finish together (72 upper tiles x 9 chunks on 148 SMs: 4.38 waves cost 4.38,
+// not 5).  Every segment ends in one FP64 partial tile, stored in slot cta * slots_per_cta + index.  The same iterator runs
+// in all warp roles, in the finishing kernel (which adds a tile's segments in chunk / stage order: bitwise reproducible)
+// and on the host (sizing).
+// ---------------------------------------------------------------------------------------------------------------------
+struct O8SegIter {
+  int n_tiles, nks, spc, n_cta, cta;
+  int n_items, full;     // items, full waves
+  int wave;              // phase A cursor
+  long posB, endB;       // phase B: range of this CTA in the remainder's (item, stage) space, stride spc per item
+  __host__ __device__ O8SegIter(int n_tiles_, int nks_, int spc_, int cta_, int n_cta_, bool remainder_only = false)
+      : n_tiles(n_tiles_), nks(nks_), spc(spc_), n_cta(n_cta_), cta(cta_) {
+    const int n_chunks = (nks + spc - 1) / spc;
+    n_items = n_tiles * n_chunks;
+    full = n_items / n_cta;
+    wave = remainder_only ? full : 0;
+    const long totalB = (long)(n_items - full * n_cta) * spc;
+    const long LB = (totalB + n_cta - 1) / n_cta;
+    posB = (long)cta * LB;
+    endB = posB + LB < totalB ? posB + LB : totalB;
+  }
+  __host__ __device__ long remainder_share() const {
+    const long totalB = (long)(n_items - full * n_cta) * spc;
+    return (totalB + n_cta - 1) / n_cta;
+  }
+  __host__ __device__ bool next(int& tile, int& k0, int& k1) {
+    if (wave < full) {
+      const int item = wave * n_cta + cta;
+      ++wave;
+      const int chunk = item / n_tiles;
+      tile = item - chunk * n_tiles;
+      k0 = chunk * spc;
+      k1 = k0 + spc < nks ? k0 + spc : nks;
+      return true;
+    }
+    while (posB < endB) {
+      const int j = (int)(posB / spc);
+      const int item = full * n_cta + j;
+      const int chunk = item / n_tiles;
+      tile = item - chunk * n_tiles;
+      const int kk = (int)(posB - (long)j * spc);
+      const long item_end = (long)(j + 1) * spc;
+      const long seg_end = item_end < endB ? item_end : endB;
+      k0 = chunk * spc + kk;
+      k1 = k0 + (int)(seg_end - posB);
+      if (k1 > nks) k1 = nks;  // a shorter last chunk
+      posB = seg_end;
+      if (k1 > k0) return true;
+    }
+    return false;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
 // SYRK partials: part[chunk][M x M] (upper 128 x 64 tiles) = X^T X over the rows of one chunk.
 //   MN = true : row-layout planes of X itself (R x M), one matrix-wide scale (*x_scale); operands MN-major.  A stage holds
 //               32 rows i of X: the A tile (128 columns j) and the B tile (64 columns) are 5-D TMA boxes (tmA, tmB) over
@@ -490,7 +548,7 @@ o8_rowquad_kernel(int n, int N, int Kd, const int8_t* __restrict__ As, const int
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool MN, bool COLL>
 __global__ void __launch_bounds__(O8_THREADS, 1)
-o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restrict__ Xs, const int* __restrict__ ex,
+o8_syrk_kernel(int M, int nks_total, int spc, int slots_per_cta, const int8_t* __restrict__ Xs, const int* __restrict__ ex,
                const double* __restrict__ x_scale, const double* __restrict__ uniform_count, double uniform_target,
                double* __restrict__ part, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   if (uniform_count && *uniform_count != uniform_target) return;  // unequal weights: handled by the correction kernels
@@ -503,20 +561,14 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rb = M / O8_BM, n_cb = M / O8_BN;
   const int n_tiles = n_rb * n_cb - n_rb * (n_rb - 1);  // sum_rb (n_cb - 2 rb): tiles with cb >= 2 rb
-  const int n_chunks = (nks_total + stages_per_chunk - 1) / stages_per_chunk;
-  const int n_items = n_tiles * n_chunks;
   const int nks_cols = M / O8_KS;  // k-steps per row block of the row layout (MN only)
-  auto decode = [&](int item, int& chunk, int& rb, int& cb, int& k0, int& k1) {
-    chunk = item / n_tiles;
-    int tl = item % n_tiles;
+  auto tile_rc = [&](int tl, int& rb, int& cb) {
     rb = 0;
     while (tl >= n_cb - 2 * rb) {
       tl -= n_cb - 2 * rb;
       ++rb;
     }
     cb = 2 * rb + tl;
-    k0 = chunk * stages_per_chunk;
-    k1 = min(nks_total, k0 + stages_per_chunk);
   };
 
   if (tid == 0) {
@@ -541,9 +593,10 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
     // ===== producer =====
     int stage = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int chunk, rb, cb, k0, k1;
-      decode(item, chunk, rb, cb, k0, k1);
+    O8SegIter it(n_tiles, nks_total, spc, blockIdx.x, gridDim.x);
+    int tl, rb, cb, k0, k1;
+    while (it.next(tl, k0, k1)) {
+      tile_rc(tl, rb, cb);
       for (int ks = k0; ks < k1; ++ks) {
         o8_mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) o8_mbar_expect_tx(&full[stage], O8_A_STAGE + O8_B_STAGE);
@@ -582,9 +635,9 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
     constexpr uint32_t lboA = MN ? 128u : (uint32_t)(O8_BM * 16), lboB = MN ? 128u : (uint32_t)(O8_BN * 16);
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int chunk, rb, cb, k0, k1;
-      decode(item, chunk, rb, cb, k0, k1);
+    O8SegIter it(n_tiles, nks_total, spc, blockIdx.x, gridDim.x);
+    int tl, k0, k1;
+    while (it.next(tl, k0, k1)) {
       o8_mbar_wait(&acc_empty, acc_phase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int ks = k0; ks < k1; ++ks) {
@@ -607,16 +660,19 @@ o8_syrk_kernel(int M, int nks_total, int stages_per_chunk, const int8_t* __restr
     const int quad = warp & 3, et = tid - 64;
     uint32_t acc_phase = 0;
     const int e_all = MN ? o8_exponent_of_scale(*x_scale) : 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int chunk, rb, cb, k0, k1;
-      decode(item, chunk, rb, cb, k0, k1);
-      const int row = rb * O8_BM + quad * 32 + lane;
+    O8SegIter it(n_tiles, nks_total, spc, blockIdx.x, gridDim.x);
+    int tl, rb, cb, k0, k1, seg = 0;
+    while (it.next(tl, k0, k1)) {
+      tile_rc(tl, rb, cb);
+      const int rloc = quad * 32 + lane;
+      const int row = rb * O8_BM + rloc;
       if (et < O8_BN) scol[et] = o8_scale_or_nan(MN ? e_all : ex[cb * O8_BN + et], 0);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       o8_mbar_wait(&acc_full, acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const double rs = o8_scale_or_nan(MN ? e_all : ex[row], -36);
-      double* prow = part + (long)chunk * M * M + (long)row * M + cb * O8_BN;
+      double* prow = part + ((long)blockIdx.x * slots_per_cta + seg) * (O8_BM * O8_BN) + rloc * O8_BN;  // slot: 128 x 64 tile
+      ++seg;
       for (int c0i = 0; c0i < O8_BN; c0i += 8) {
         uint32_t g[O8_NS][8];
 #pragma unroll
@@ -649,40 +705,86 @@ __device__ __forceinline__ double o8_entry(const int8_t* __restrict__ digits, in
   return (double)y;
 }
 
-// Out (symmetric) (+)= alpha * w0 * (sum_chunks part[chunk] - sum_{i in skip} x_i x_i^T), chunks added in index order
-// (bitwise reproducible).  skip (optional): rows whose weight is 0 instead of w0 (rows of the SVGP step whose predictive
-// variance was clamped: their gradient is zero), rebuilt from the digit planes; normally empty.
-__global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int n_chunks, const double* __restrict__ part, double alpha,
+// Out (symmetric) (+)= alpha * w0 * (sum of the tile's segment partials - sum_{i in skip} x_i x_i^T).  One CTA per upper
+// 128 x 64 tile; the segments of the tile are found by re-running the CTAs' segment iterators (a handful of integer steps)
+// and added in CTA / index order (bitwise reproducible).  skip (optional): rows whose weight is 0 instead of w0 (rows of the
+// SVGP step whose predictive variance was clamped: their gradient is zero), rebuilt from the digit planes; normally empty.
+__global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_total, int spc, int n_cta, int slots_per_cta,
+                                                             const double* __restrict__ part, double alpha,
                                                              const double* __restrict__ w0, const double* __restrict__ uniform_count,
                                                              double uniform_target, int accumulate, double* __restrict__ Out,
                                                              long ldo, const int* __restrict__ skip_count,
                                                              const int* __restrict__ skip_rows, const int8_t* __restrict__ digits,
                                                              const double* __restrict__ x_scale) {
   if (uniform_count && *uniform_count != uniform_target) return;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (r >= M || c >= M || c < r) return;
-  double s = 0.0;
-  for (int ch = 0; ch < n_chunks; ++ch) s += part[(long)ch * M * M + (long)r * M + c];
-  if (skip_count) {
-    const int ns = *skip_count;
-    if (ns > 0) {
-      const int e = o8_exponent_of_scale(*x_scale);
-      const double sc2 = o8_pow2(2 * (e - O8_FRAC));
+  const int n_rb = M / O8_BM, n_cb = M / O8_BN;
+  const int n_tiles = n_rb * n_cb - n_rb * (n_rb - 1);
+  const int tile = blockIdx.x;
+  int rb = 0, tl = tile;
+  while (tl >= n_cb - 2 * rb) {
+    tl -= n_cb - 2 * rb;
+    ++rb;
+  }
+  const int cb = 2 * rb + tl;
+  constexpr int EPT = O8_BM * O8_BN / 256;  // elements per thread: e = threadIdx.x + 256 i (coalesced)
+  double acc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) acc[i] = 0.0;
+  {
+    const O8SegIter probe(n_tiles, nks_total, spc, 0, n_cta);
+    const int n_chunks = (nks_total + spc - 1) / spc;
+    const long LB = probe.remainder_share();
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int item = chunk * n_tiles + tile;
+      if (item < probe.full * n_cta) {  // a full-wave item: one segment, owned by CTA item % n_cta as its (item / n_cta)-th
+        const double* src = part + ((long)(item % n_cta) * slots_per_cta + item / n_cta) * (O8_BM * O8_BN) + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) acc[i] += src[256 * i];
+        continue;
+      }
+      // an item of the remainder: its stages are spread over the CTAs c_first .. c_last
+      const int j = item - probe.full * n_cta;
+      const int c_first = (int)(((long)j * spc) / LB), c_last = (int)((((long)j + 1) * spc - 1) / LB);
+      for (int c = c_first; c <= c_last && c < n_cta; ++c) {
+        O8SegIter it(n_tiles, nks_total, spc, c, n_cta, true);
+        int t2, k0, k1, idx = probe.full;
+        while (it.next(t2, k0, k1)) {
+          if (t2 == tile && k0 / spc == chunk) {
+            const double* src = part + ((long)c * slots_per_cta + idx) * (O8_BM * O8_BN) + threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) acc[i] += src[256 * i];
+          }
+          ++idx;
+        }
+      }
+    }
+  }
+  const int n_skip = skip_count ? *skip_count : 0;
+  const double scale = alpha * (w0 ? w0[0] : 1.0);
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = threadIdx.x + 256 * i;
+    const int r = rb * O8_BM + e / O8_BN, c = cb * O8_BN + e % O8_BN;
+    if (c < r) continue;
+    double s = acc[i];
+    if (n_skip > 0) {
+      const int ex = o8_exponent_of_scale(*x_scale);
+      const double sc2 = o8_pow2(2 * (ex - O8_FRAC));
       double corr = 0.0;
-      for (int t = 0; t < ns; ++t) {
-        const int i = skip_rows[t];
-        corr = fma(o8_entry(digits, M / O8_KS, i, r), o8_entry(digits, M / O8_KS, i, c), corr);
+      for (int t = 0; t < n_skip; ++t) {
+        const int ii = skip_rows[t];
+        corr = fma(o8_entry(digits, M / O8_KS, ii, r), o8_entry(digits, M / O8_KS, ii, c), corr);
       }
       s -= corr * sc2;
     }
-  }
-  s *= alpha * (w0 ? w0[0] : 1.0);
-  if (accumulate) {
-    Out[(long)r * ldo + c] += s;
-    if (c != r) Out[(long)c * ldo + r] += s;
-  } else {
-    Out[(long)r * ldo + c] = s;
-    Out[(long)c * ldo + r] = s;
+    s *= scale;
+    if (accumulate) {
+      Out[(long)r * ldo + c] += s;
+      if (c != r) Out[(long)c * ldo + r] += s;
+    } else {
+      Out[(long)r * ldo + c] = s;
+      Out[(long)c * ldo + r] = s;
+    }
   }
 }
 
@@ -715,25 +817,29 @@ __global__ void __launch_bounds__(256) o8_sum_partials_kernel(int nb, int N, con
   }
 }
 
-static int o8_syrk_chunks(int nks, int n_tiles, int* spc_out) {
-  // chunks of at most O8_CHUNK_STAGES stages (int32 exactness); among the admissible chunk counts take the one whose work
-  // items fill whole rounds of the persistent CTAs best (cost = rounds x stages per chunk)
-  const int min_chunks = ceil_div(nks, O8_CHUNK_STAGES);
-  int best_chunks = min_chunks;
-  long best_cost = -1;
-  for (int c = min_chunks; c <= min_chunks + 64 && c <= nks; ++c) {
-    const int spc_c = ceil_div(nks, c);
-    if (spc_c < 16 && c > min_chunks) break;
-    const long rounds = ((long)n_tiles * ceil_div(nks, spc_c) + kNumSMs - 1) / kNumSMs;
-    const long cost = rounds * (spc_c + 4);  // + epilogue, in units of a k-stage
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best_chunks = c;
-    }
-  }
+// Launch shape of the SYRK: CTAs, stages per row chunk and the largest number of segments any CTA produces (host run of the
+// device iterator).  The chunk length is the largest that (i) keeps int32 exact (O8_MAX_SEG) and (ii) lets the rows a wave
+// of CTAs works on (kNumSMs / n_tiles chunks) stay resident in L2 (~110 MB of the 126 MB): every extra chunk costs one
+// more epilogue per CTA, too long a chunk turns the kernel DRAM bound.
+static int o8_syrk_shape(int nks, int n_tiles, int M, int* n_cta_out, int* spc_out) {
+  const double bytes_per_stage = (double)kNumSMs / n_tiles * O8_KS * (double)M * O8_NS;  // of the chunks in flight
+  int max_spc = (int)(110e6 / bytes_per_stage);
+  if (max_spc > O8_MAX_SEG) max_spc = O8_MAX_SEG;
+  if (max_spc < 32) max_spc = 32;
+  const int best_chunks = ceil_div(nks, max_spc);
   const int spc = ceil_div(nks, best_chunks);
+  const long items = (long)n_tiles * ceil_div(nks, spc);
+  const int n_cta = (int)(items < kNumSMs ? items : kNumSMs);
+  int worst = 1;
+  for (int c = 0; c < n_cta; ++c) {
+    O8SegIter it(n_tiles, nks, spc, c, n_cta);
+    int t, k0, k1, cnt = 0;
+    while (it.next(t, k0, k1)) ++cnt;
+    if (cnt > worst) worst = cnt;
+  }
+  *n_cta_out = n_cta;
   *spc_out = spc;
-  return ceil_div(nks, spc);
+  return worst;
 }
 
 static inline int o8_syrk_tiles(int M) {
@@ -873,10 +979,10 @@ extern "C" int npgp_rowquad_i8_gemm_only(int n, int M, const double* K, long ldk
 // bytes of the partial-sum workspace of npgp_o8_syrk_digits for n contraction rows
 extern "C" long npgp_o8_syrk_part_bytes(int n, int M) {
   if (n <= 0 || M <= 0 || M % O8_BM) return 0;
-  int spc;
+  int n_cta, spc;
   const int nks = ceil_div(((long)n + O8_BM - 1) / O8_BM * O8_BM, O8_KS);
-  const int n_chunks = o8_syrk_chunks(nks, o8_syrk_tiles(M), &spc);
-  return (long)n_chunks * M * M * (long)sizeof(double);
+  const int slots = o8_syrk_shape(nks, o8_syrk_tiles(M), M, &n_cta, &spc);
+  return (long)n_cta * slots * (O8_BM * O8_BN) * (long)sizeof(double);
 }
 
 // 5-D tensor map over the A-type digit planes of X (n_rb row blocks x M columns) for the MN-major SYRK tiles, in units of
@@ -922,20 +1028,17 @@ static int o8_syrk_launch(int M, int nks, const int8_t* Xs, const int* ex, const
     if (rc) return rc;
   }
   const int n_tiles = o8_syrk_tiles(M);
-  int spc;
-  const int n_chunks = o8_syrk_chunks(nks, n_tiles, &spc);
-  const int items = n_tiles * n_chunks;
-  const int grid = items < kNumSMs ? items : kNumSMs;
+  int grid, spc;
+  const int slots = o8_syrk_shape(nks, n_tiles, M, &grid, &spc);
   if (g_o8_collector)
-    o8_syrk_kernel<MN, true><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, Xs, ex, x_scale, uniform_count,
+    o8_syrk_kernel<MN, true><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, slots, Xs, ex, x_scale, uniform_count,
                                                                       uniform_target, part, tmA, tmB);
   else
-    o8_syrk_kernel<MN, false><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, Xs, ex, x_scale, uniform_count,
+    o8_syrk_kernel<MN, false><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, slots, Xs, ex, x_scale, uniform_count,
                                                                        uniform_target, part, tmA, tmB);
   NPGP_LAUNCH_CHECK();
-  dim3 grd(ceil_div(M, 32), ceil_div(M, 8));
-  o8_syrk_finish_kernel<<<grd, 256, 0, stream>>>(M, n_chunks, part, alpha, w0_dev, uniform_count, uniform_target, accumulate,
-                                                 Out, ldo, skip_count, skip_rows, MN ? Xs : nullptr, x_scale);
+  o8_syrk_finish_kernel<<<n_tiles, 256, 0, stream>>>(M, nks, spc, grid, slots, part, alpha, w0_dev, uniform_count, uniform_target,
+                                                     accumulate, Out, ldo, skip_count, skip_rows, MN ? Xs : nullptr, x_scale);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

@@ -548,6 +548,9 @@ class RbfMatvecFn(torch.autograd.Function):
         return None, dz, None, None, dV if ctx.needs_input_grad[4] else None, None, None
 
 
+ROWQUAD_SYM_I8 = True  # rowquad_sym's forward product on the int8 tensor cores when the width allows (DGP layers)
+
+
 class RowquadFn(torch.autograd.Function):
     """q_i = k_i^T C k_i for SYMMETRIC C (T = K C on the FP64 tensor pipe with the row-dot fused in the epilogue).
     Backward: dK = 2 diag(dq) T,  dC = K^T diag(dq) K (wsyrk)."""
@@ -555,7 +558,11 @@ class RowquadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, K, Cm):
         Kc, Cc = K.detach().contiguous(), Cm.detach().contiguous()
-        T, q = rowquad(Kc, Cc)
+        if ROWQUAD_SYM_I8 and Kc.shape[1] % 64 == 0 and Kc.shape[0] >= 4096:
+            # exact byte-digit split on the integer tensor cores (same result to FP64 rounding, ~2.4x the DMMA rate)
+            T, q = rowquad_i8(Kc, Cc)
+        else:
+            T, q = rowquad(Kc, Cc)
         ctx.save_for_backward(Kc, T)
         return q
 
