@@ -239,6 +239,7 @@ int npgp_o8_syrk_digits(int n, int M, const void* x_digits, const double* x_scal
                         const int* skip_count, const int* skip_rows, int accumulate, double* Out, long ldo, void* part,
                         long part_bytes, npgp_stream_t stream);
 int npgp_o8_set_collector(int on); /* measurement switch: A-operand collector reuse hints (default 1) */
+int npgp_o8_set_syrk_split(int on); /* measurement switch: split the SYRK's last partial wave evenly over the CTAs (default 1) */
 
 /* Deterministic (two-stage, fixed order) variants of the ELBO reductions used with the digit-plane path. */
 int npgp_mu_gmu_parts(int n, const double* y, const double* mu_part, int nparts, long stride, const double* noise,

@@ -52,6 +52,7 @@ _SIGS = {
     "npgp_wsyrk_weighted_only": ([_i, _i, _d, _p, _l, _p, _p, _d, _p, _l, _p], _i),
     "npgp_rowquad_i8": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p, _l, _p], _i),
     "npgp_o8_set_collector": ([_i], _i),
+    "npgp_o8_set_syrk_split": ([_i], _i),
     "npgp_o8_digits_bytes": ([_i, _i, _i], _l),
     "npgp_o8_slice_rows": ([_i, _i, _p, _l, _i, _p, _p, _p], _i),
     "npgp_o8_rowquad_digits": ([_i, _i, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _l, _p, _p, _p], _i),

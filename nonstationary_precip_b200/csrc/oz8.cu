@@ -494,22 +494,27 @@ struct O8SegIter {
   int n_items, full;     // items, full waves
   int wave;              // phase A cursor
   long posB, endB;       // phase B: range of this CTA in the remainder's (item, stage) space, stride spc per item
+  // spc_ < 0: measurement switch, whole items only (the last wave stays partial, as before the remainder split)
   __host__ __device__ O8SegIter(int n_tiles_, int nks_, int spc_, int cta_, int n_cta_, bool remainder_only = false)
-      : n_tiles(n_tiles_), nks(nks_), spc(spc_), n_cta(n_cta_), cta(cta_) {
+      : n_tiles(n_tiles_), nks(nks_), spc(spc_ < 0 ? -spc_ : spc_), n_cta(n_cta_), cta(cta_) {
     const int n_chunks = (nks + spc - 1) / spc;
     n_items = n_tiles * n_chunks;
-    full = n_items / n_cta;
+    full = spc_ < 0 ? (n_items + n_cta - 1) / n_cta : n_items / n_cta;
     wave = remainder_only ? full : 0;
-    const long totalB = (long)(n_items - full * n_cta) * spc;
+    long totalB = (long)(n_items - full * n_cta) * spc;
+    if (totalB < 0) totalB = 0;
     const long LB = (totalB + n_cta - 1) / n_cta;
     posB = (long)cta * LB;
     endB = posB + LB < totalB ? posB + LB : totalB;
   }
   __host__ __device__ long remainder_share() const {
-    const long totalB = (long)(n_items - full * n_cta) * spc;
-    return (totalB + n_cta - 1) / n_cta;
+    long totalB = (long)(n_items - full * n_cta) * spc;
+    if (totalB < 0) totalB = 0;
+    const long lb = (totalB + n_cta - 1) / n_cta;
+    return lb > 0 ? lb : 1;
   }
   __host__ __device__ bool next(int& tile, int& k0, int& k1) {
+    while (wave < full && wave * n_cta + cta >= n_items) ++wave;  // (only with the measurement switch)
     if (wave < full) {
       const int item = wave * n_cta + cta;
       ++wave;
@@ -732,7 +737,8 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
   for (int i = 0; i < EPT; ++i) acc[i] = 0.0;
   {
     const O8SegIter probe(n_tiles, nks_total, spc, 0, n_cta);
-    const int n_chunks = (nks_total + spc - 1) / spc;
+    const int aspc = probe.spc;  // (spc < 0 carries the measurement switch)
+    const int n_chunks = (nks_total + aspc - 1) / aspc;
     const long LB = probe.remainder_share();
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int item = chunk * n_tiles + tile;
@@ -744,12 +750,12 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
       }
       // an item of the remainder: its stages are spread over the CTAs c_first .. c_last
       const int j = item - probe.full * n_cta;
-      const int c_first = (int)(((long)j * spc) / LB), c_last = (int)((((long)j + 1) * spc - 1) / LB);
+      const int c_first = (int)(((long)j * aspc) / LB), c_last = (int)((((long)j + 1) * aspc - 1) / LB);
       for (int c = c_first; c <= c_last && c < n_cta; ++c) {
         O8SegIter it(n_tiles, nks_total, spc, c, n_cta, true);
         int t2, k0, k1, idx = probe.full;
         while (it.next(t2, k0, k1)) {
-          if (t2 == tile && k0 / spc == chunk) {
+          if (t2 == tile && k0 / aspc == chunk) {
             const double* src = part + ((long)c * slots_per_cta + idx) * (O8_BM * O8_BN) + threadIdx.x;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) acc[i] += src[256 * i];
@@ -817,6 +823,8 @@ __global__ void __launch_bounds__(256) o8_sum_partials_kernel(int nb, int N, con
   }
 }
 
+static int g_o8_syrk_whole_items = 0;  // measurement switch (npgp_o8_set_syrk_split(0)): no split of the last partial wave
+
 // Launch shape of the SYRK: CTAs, stages per row chunk and the largest number of segments any CTA produces (host run of the
 // device iterator).  The chunk length is the largest that (i) keeps int32 exact (O8_MAX_SEG) and (ii) lets the rows a wave
 // of CTAs works on (kNumSMs / n_tiles chunks) stay resident in L2 (~110 MB of the 126 MB): every extra chunk costs one
@@ -832,13 +840,13 @@ static int o8_syrk_shape(int nks, int n_tiles, int M, int* n_cta_out, int* spc_o
   const int n_cta = (int)(items < kNumSMs ? items : kNumSMs);
   int worst = 1;
   for (int c = 0; c < n_cta; ++c) {
-    O8SegIter it(n_tiles, nks, spc, c, n_cta);
+    O8SegIter it(n_tiles, nks, g_o8_syrk_whole_items ? -spc : spc, c, n_cta);
     int t, k0, k1, cnt = 0;
     while (it.next(t, k0, k1)) ++cnt;
     if (cnt > worst) worst = cnt;
   }
   *n_cta_out = n_cta;
-  *spc_out = spc;
+  *spc_out = g_o8_syrk_whole_items ? -spc : spc;
   return worst;
 }
 
@@ -859,6 +867,12 @@ extern "C" void npgp_rowquad_i8_debug(long long* dev_counters) { g_o8_dbg = dev_
 // measurement switch: 1 (default) = A-operand collector reuse hints on the digit products, 0 = plain MMAs
 extern "C" int npgp_o8_set_collector(int on) {
   g_o8_collector = on ? 1 : 0;
+  return NPGP_OK;
+}
+
+// measurement switch: 1 (default) = the items of the last partial wave of the SYRK are split evenly over the CTAs, 0 = whole items
+extern "C" int npgp_o8_set_syrk_split(int on) {
+  g_o8_syrk_whole_items = on ? 0 : 1;
   return NPGP_OK;
 }
 

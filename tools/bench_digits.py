@@ -81,6 +81,10 @@ def main():
         report("o8_syrk_digits[collector=%d] (MN-major planes, finish included)" % coll, ms, best,
                int8_tops_useful=round(28 * B * M * (M + 64) / best / 1e9, 1))
     ops.set_i8_collector(True)
+    for split in (0, 1, 0, 1):
+        check(lib().npgp_o8_set_syrk_split(split), "split")
+        ms, best = timeit(lambda: ops.o8_syrk_digits(B, M, digits, s, part, out=Out))
+        report("o8_syrk_digits[remainder split=%d]" % split, ms, best, int8_tops_useful=round(28 * B * M * (M + 64) / best / 1e9, 1))
     Kf = ops.gibbs_full_fwd(x, Sx, z, Sz, 1e-5, s)
     ms, best = timeit(lambda: ops.rowquad_i8(Kf, C, T=T))
     report("rowquad_i8 (general operands: slicing passes included)", ms, best)
