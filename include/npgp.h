@@ -309,6 +309,7 @@ int npgp_comm_unique_id(void* id128);
 int npgp_comm_create(void** comm, const void* id128, int nranks, int rank);
 int npgp_comm_destroy(void* comm);
 int npgp_allreduce_f64(void* comm, double* buf, long n, npgp_stream_t stream);
+int npgp_allreduce_f64_pair(void* comm, double* buf1, long n1, double* buf2, long n2, npgp_stream_t stream); /* one grouped launch */
 
 /* ---- measurement helpers (csrc/peak.cu): FP64 ceiling probes (mode 0 = DFMA loop, 1 = DMMA.8x8x4 loop) and the int8
  * tensor-core ceiling (blocks x reps x 8 back-to-back tcgen05.mma kind::i8 of 128 x n_tile x 32 from resident shared

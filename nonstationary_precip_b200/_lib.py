@@ -103,6 +103,7 @@ _SIGS = {
     "npgp_comm_create": ([_p, _p, _i, _i], _i),
     "npgp_comm_destroy": ([_p], _i),
     "npgp_allreduce_f64": ([_p, _p, _l, _p], _i),
+    "npgp_allreduce_f64_pair": ([_p, _p, _l, _p, _l, _p], _i),
 }
 
 _lib = None

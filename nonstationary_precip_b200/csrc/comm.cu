@@ -18,6 +18,7 @@ typedef int (*fn_get_unique_id)(NcclId*);
 typedef int (*fn_comm_init_rank)(NcclComm*, int, NcclId, int);
 typedef int (*fn_comm_destroy)(NcclComm);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*fn_group)(void);
 
 struct NcclApi {
   void* handle = nullptr;
@@ -25,6 +26,7 @@ struct NcclApi {
   fn_comm_init_rank comm_init_rank = nullptr;
   fn_comm_destroy comm_destroy = nullptr;
   fn_all_reduce all_reduce = nullptr;
+  fn_group group_start = nullptr, group_end = nullptr;
 };
 
 // resolved once per process (read-only afterwards)
@@ -42,9 +44,13 @@ const NcclApi* nccl_api() {
       api.comm_init_rank = reinterpret_cast<fn_comm_init_rank>(dlsym(h, "ncclCommInitRank"));
       api.comm_destroy = reinterpret_cast<fn_comm_destroy>(dlsym(h, "ncclCommDestroy"));
       api.all_reduce = reinterpret_cast<fn_all_reduce>(dlsym(h, "ncclAllReduce"));
+      api.group_start = reinterpret_cast<fn_group>(dlsym(h, "ncclGroupStart"));
+      api.group_end = reinterpret_cast<fn_group>(dlsym(h, "ncclGroupEnd"));
     }
   }
-  return (api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.all_reduce) ? &api : nullptr;
+  return (api.get_unique_id && api.comm_init_rank && api.comm_destroy && api.all_reduce && api.group_start && api.group_end)
+             ? &api
+             : nullptr;
 }
 
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;
@@ -86,4 +92,19 @@ extern "C" int npgp_allreduce_f64(void* comm, double* buf, long n, cudaStream_t 
   const NcclApi* api = nccl_api();
   if (!api) return NPGP_EUNSUPPORTED;
   return api->all_reduce(buf, buf, (size_t)n, kNcclFloat64, kNcclSum, comm, stream) == 0 ? NPGP_OK : NPGP_EINVAL;
+}
+
+/* two disjoint pieces in ONE grouped launch (the head and the tail of the flat gradient buffer around the part that was
+ * reduced early, csrc/svgp_step.cu); either piece may be empty */
+extern "C" int npgp_allreduce_f64_pair(void* comm, double* buf1, long n1, double* buf2, long n2, cudaStream_t stream) {
+  if (!comm || n1 < 0 || n2 < 0 || (n1 > 0 && !buf1) || (n2 > 0 && !buf2)) return NPGP_EINVAL;
+  if (n1 == 0) return npgp_allreduce_f64(comm, buf2, n2, stream);
+  if (n2 == 0) return npgp_allreduce_f64(comm, buf1, n1, stream);
+  const NcclApi* api = nccl_api();
+  if (!api) return NPGP_EUNSUPPORTED;
+  int rc = api->group_start();
+  if (rc == 0) rc = api->all_reduce(buf1, buf1, (size_t)n1, kNcclFloat64, kNcclSum, comm, stream);
+  if (rc == 0) rc = api->all_reduce(buf2, buf2, (size_t)n2, kNcclFloat64, kNcclSum, comm, stream);
+  const int rc2 = api->group_end();
+  return (rc == 0 && rc2 == 0) ? NPGP_OK : NPGP_EINVAL;
 }

@@ -16,6 +16,8 @@ dev = torch.device("cuda", 0)
 x_h, y_h, perm = bench.make_data(bench.N_TOTAL, bench.DIM)
 kw = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.make_params(variant, bench.M_IND, bench.DIM).items()}
 model = SVGPGibbs(variant, x_h[perm[:bench.M_IND]].to(dev), bench.N_TOTAL, **kw)
+if os.environ.get("ENGINE", "c") == "c":
+    model.use_c_engine()  # the whole step is one C call (npgp_svgp_step)
 X, Y = x_h[:B].to(dev), y_h[:B].to(dev)
 for _ in range(2):
     model.train_step(X, Y)
