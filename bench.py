@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 N_TOTAL, M_IND, B_GLOBAL, DIM = 1 << 20, 1024, 65536, 3
 # dram__bytes_read.sum + dram__bytes_write.sum of one o8_rowquad_kernel launch at Bl = 65536 from the ncu --set full capture
 # summarised in profiles/ (None until that capture exists for the current kernel)
-TRAFFIC_ROWQUAD_BYTES = None
+TRAFFIC_ROWQUAD_BYTES = 983.2e6  # dram__bytes_read.sum + dram__bytes_write.sum of o8_rowquad_kernel at the C2 shapes, one launch:
+# 477.8 + 505.4 MB (profiles/r02_ncu_full_step_kernels_final.txt)
 
 
 def env_int(k, d):
