@@ -99,6 +99,11 @@ int npgp_wsyrk(int n, int M, double alpha, const double* K, long ldk, const doub
 int npgp_wsyrk_hint(int n, int M, double alpha, const double* K, long ldk, const double* w, const double* uniform_count,
                     double uniform_target, double* Out, long ldo, npgp_stream_t stream);
 int npgp_symmetrize(int M, double* C, long ldc, int from_upper, npgp_stream_t stream);
+/* Triangular solve through the inverse factor P = L^-1 of npgp_potrf_inv_*: X = P B (trans 0) or P^T B (trans 1), one
+ * triangular-aware product -- the reference's inv_root = triangular_solve(eye, chol); k_ux1.matmul(inv_root)
+ * (models/gibbs_kernels.py:205-208,222-225).  B, X (M,k). */
+int npgp_trsm(int trans, int M, int k, const double* P, long ldp, const double* B, long ldb, double* X, long ldx,
+              npgp_stream_t stream);
 /* measurement switch for the GEMM family: 0 = 128x128 tiles (1 CTA/SM), 1/2 = 128x64 (2 CTAs/SM), 3/4 = 64x64 tiles with
  * 4-warp CTAs (3/4 CTAs/SM), 5 = auto (default) */
 int npgp_set_gemm_config(int cfg);

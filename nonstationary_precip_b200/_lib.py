@@ -68,6 +68,7 @@ _SIGS = {
     "npgp_wsyrk": ([_i, _i, _d, _p, _l, _p, _p, _l, _p], _i),
     "npgp_wsyrk_hint": ([_i, _i, _d, _p, _l, _p, _p, _d, _p, _l, _p], _i),
     "npgp_symmetrize": ([_i, _p, _l, _i, _p], _i),
+    "npgp_trsm": ([_i, _i, _i, _p, _l, _p, _l, _p, _l, _p], _i),
     "npgp_potrf_workspace_bytes": ([_i], _l),
     "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_potrf_flow_workspace_bytes": ([_i], _l),

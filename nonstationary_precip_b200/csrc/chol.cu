@@ -170,13 +170,10 @@ static long work_doubles(int M) {
 }
 
 int potrf_inv_impl(int M, double* A, long lda, double* P, long ldp, double* work, int* info, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    NPGP_CUDA(cudaFuncSetAttribute(potrf_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
-    NPGP_CUDA(cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
-    NPGP_CUDA(cudaFuncSetAttribute(trinv_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
-    attr_set = true;
-  }
+  // (the attribute is per device and the call is cheap: set on every call, so a process that touches a second GPU is fine)
+  NPGP_CUDA(cudaFuncSetAttribute(potrf_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
+  NPGP_CUDA(cudaFuncSetAttribute(potrf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM));
+  NPGP_CUDA(cudaFuncSetAttribute(trinv_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEVEL_SMEM));
   const int nblk = (M + TB - 1) / TB;
   double* L = work;  // M x M, ld = M
   const long ldl = M + (M & 1);

@@ -315,12 +315,9 @@ static int launch_cfg(const GemmParams& p, cudaStream_t st) {
   constexpr int GEMM_THREADS = Cfg::NT;
   auto kern = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, false, Cfg::MINB, Cfg::NT>;
   auto kern_w = dgemm_kernel<Cfg::BM, Cfg::BN, Cfg::WM, Cfg::WN, Cfg::BK, Cfg::ST, AK, BK_, true, Cfg::MINB, Cfg::NT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NPGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    NPGP_CUDA(cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  // per-device attribute, cheap call: set every time (a process may touch more than one GPU)
+  NPGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  NPGP_CUDA(cudaFuncSetAttribute(kern_w, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(ceil_div(p.N, Cfg::BN), ceil_div(p.M, Cfg::BM), p.splits);
   if (p.w && p.w_uniform_count) {
     if (!p.weighted_only) {
@@ -502,4 +499,16 @@ extern "C" int npgp_set_gemm_config(int cfg) {
   if (cfg < 0 || cfg > 5) return NPGP_EINVAL;
   npgp::g_gemm_cfg = cfg;
   return NPGP_OK;
+}
+
+// X = op(L)^-1 B through the inverse factor P = L^-1 that npgp_potrf_inv_* return: one triangular-aware DMMA product,
+// X = P B (trans = 0) or X = P^T B (trans = 1).  This is what the reference does with its Cholesky factor --
+// inv_root = triangular_solve(eye, chol) followed by matmul (models/gibbs_kernels.py:205-208,222-225) -- and what GPyTorch's
+// whitened strategy needs (L^-1 Kzx).  P (M x M, lower), B, X (M x k); ldb, ldx even, 16-byte aligned operands.
+extern "C" int npgp_trsm(int trans, int M, int k, const double* P, long ldp, const double* B, long ldb, double* X, long ldx,
+                         cudaStream_t stream) {
+  if (M < 0 || k < 0 || (trans != 0 && trans != 1)) return NPGP_EINVAL;
+  if (M == 0 || k == 0) return NPGP_OK;
+  if (!P || !B || !X || ldp < M || ldb < k || ldx < k) return NPGP_EINVAL;
+  return npgp_dgemm(trans, 0, M, k, M, 1.0, P, ldp, B, ldb, 0.0, X, ldx, trans ? 2 : 1, 0, 0, stream);
 }

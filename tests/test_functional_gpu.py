@@ -41,3 +41,22 @@ def test_op_dot_mv_t(via_compat):
     vr = v.clone().requires_grad_(True)
     fn.mv(S, vr, invert=True).sum().backward()
     assert ((vr.grad - torch.linalg.solve(S, torch.ones(300, device="cuda"))).abs().max()).item() < 1e-10
+
+
+@pytest.mark.parametrize("M,k", [(200, 6), (512, 64)])
+def test_trsm_through_the_inverse_factor(M, k):
+    """npgp_trsm: X = L^-1 B / L^-T B with P = L^-1 from npgp_potrf_inv_* (the reference's triangular_solve(eye, chol) + matmul,
+    models/gibbs_kernels.py:205-208,222-225) against torch.linalg.solve_triangular."""
+    from nonstationary_precip_b200 import ops
+    from nonstationary_precip_b200._lib import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, M, generator=g, dtype=torch.float64)
+    K = (A @ A.T / M + torch.eye(M, dtype=torch.float64)).cuda()
+    L, P, info = ops.potrf_inv(K.clone())
+    assert int(info) == 0
+    B = torch.randn(M, k, generator=g, dtype=torch.float64).cuda()
+    for trans in (0, 1):
+        X = torch.empty_like(B)
+        check(lib().npgp_trsm(trans, M, k, ptr(P), P.stride(0), ptr(B), B.stride(0), ptr(X), X.stride(0), stream()), "npgp_trsm")
+        want = torch.linalg.solve_triangular(L.T if trans else L, B, upper=bool(trans))
+        assert ((X - want).abs().max() / want.abs().max()).item() < 1e-12

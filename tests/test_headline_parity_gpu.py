@@ -40,15 +40,20 @@ def to_dev(kw):
     return {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
 
 
-@pytest.mark.parametrize("impl", ["i8", "dmma"])
+@pytest.mark.parametrize("impl", ["c-step", "i8", "dmma"])
 @pytest.mark.parametrize("variant", ["full", "diag"])
 @pytest.mark.parametrize("trained", [False, True])
 def test_headline_elbo_and_gradients(variant, impl, trained):
+    """impl: "c-step" = npgp_svgp_elbo_fwd/_bwd (the bench's path: one C call per pass, digit planes); "i8" / "dmma" = the
+    Python orchestration with the exact int8 / the FP64 DMMA contractions."""
     from nonstationary_precip_b200.svgp import SVGPGibbs
     rows = 8192
     x, y, Z, kw = headline_problem(variant, rows, trained_state=trained)
     model = SVGPGibbs(variant, Z.cuda(), N_TOTAL, **to_dev(kw))
-    model.rowquad_impl = impl
+    if impl == "c-step":
+        model.use_c_engine()
+    else:
+        model.rowquad_impl = impl
     loss = model.loss_and_grad(x.cuda(), y.cuda())
     assert int(model.last["info"]) == 0
     want_loss, want = oracle_loss_and_grads(variant, x, y, Z, kw, N_TOTAL)
