@@ -73,6 +73,7 @@ _SIGS = {
     "npgp_potrf_inv_lower": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_potrf_flow_workspace_bytes": ([_i], _l),
     "npgp_potrf_inv_flow": ([_i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
+    "npgp_potrf_inv_flow_batch": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
     "npgp_i8_peak_probe": ([_i, _i, _i, _i, _p], _i),
     "npgp_set_gemm_config": ([_i], _i),

@@ -87,9 +87,25 @@ __device__ __forceinline__ void zero_tile_global(double* __restrict__ G, long ld
 }
 
 // flags: [0, nb^2) L tiles (i * nb + k), [nb^2, 2 nb^2) P tiles, [2 nb^2] abort
-__global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, double* __restrict__ A, long lda,
-                                                           double* __restrict__ P, long ldp, int* __restrict__ flags,
-                                                           int* __restrict__ info) {
+// Up to kFlowBatch independent matrices of the same order are factored by ONE launch: CTA x works on matrix x % n, task
+// x / n.  Interleaving keeps every matrix's own task order (dependencies still point to lower block indices), and the early
+// (critical-path) tasks of ALL matrices are resident from the start -- two concurrent single-matrix launches instead
+// queue the second matrix's CTAs behind the first one's resident waiters (0.62 ms for two against 0.43 for one).
+constexpr int kFlowBatch = 4;
+struct FlowBatch {
+  double* A[kFlowBatch];
+  double* P[kFlowBatch];
+  int* flags[kFlowBatch];
+  int* info[kFlowBatch];
+  int n;
+};
+
+__global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, const FlowBatch fb, long lda, long ldp) {
+  const int which = blockIdx.x % fb.n;
+  double* __restrict__ A = fb.A[which];
+  double* __restrict__ P = fb.P[which];
+  int* __restrict__ flags = fb.flags[which];
+  int* __restrict__ info = fb.info[which];
   extern __shared__ double sm[];
   double *bufA = sm, *bufB = sm + TILE_SMEM, *bufC = sm + 2 * TILE_SMEM;
   int* Lf = flags;
@@ -97,7 +113,7 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, double
   int* abort_flag = flags + 2 * nb * nb;
   const WarpPos p;
   const int nL = nb * (nb + 1) / 2;
-  int t = blockIdx.x;
+  int t = blockIdx.x / fb.n;
   if (t < nL) {
     // ---- L task: tile (i,k), column-major numbering
     int k = 0;
@@ -205,7 +221,36 @@ extern "C" int npgp_potrf_inv_flow(int M, double* A, long lda, double* P, long l
   NPGP_CUDA(cudaFuncSetAttribute(potrf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_SMEM));
   NPGP_CUDA(cudaMemsetAsync(work, 0, (size_t)npgp_potrf_flow_workspace_bytes(M), stream));
   NPGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int), stream));
-  potrf_flow_kernel<<<nb * nb, CT, FLOW_SMEM, stream>>>(M, nb, A, lda, P, ldp, static_cast<int*>(work), info);
+  FlowBatch fb;
+  fb.n = 1;
+  fb.A[0] = A, fb.P[0] = P, fb.flags[0] = static_cast<int*>(work), fb.info[0] = info;
+  potrf_flow_kernel<<<nb * nb, CT, FLOW_SMEM, stream>>>(M, nb, fb, lda, ldp);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// The same for n <= 4 independent matrices of order M in ONE launch (host arrays of device pointers; work[i]: flags of matrix
+// i, npgp_potrf_flow_workspace_bytes(M) bytes each; info[i] as above).  All matrices share lda / ldp.
+extern "C" int npgp_potrf_inv_flow_batch(int n, int M, double* const* A, long lda, double* const* P, long ldp,
+                                         void* const* work, long work_bytes, int* const* info, cudaStream_t stream) {
+  if (n < 1 || n > kFlowBatch || M < 0 || !A || !P || !work || !info) return NPGP_EINVAL;
+  if (M == 0) return NPGP_OK;
+  if ((lda & 1) || (ldp & 1)) return NPGP_EUNSUPPORTED;
+  if (work_bytes < npgp_potrf_flow_workspace_bytes(M)) return NPGP_EWORKSPACE;
+  FlowBatch fb;
+  fb.n = n;
+  for (int i = 0; i < n; ++i) {
+    if (!A[i] || !P[i] || !work[i] || !info[i]) return NPGP_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(A[i]) & 15) || (reinterpret_cast<uintptr_t>(P[i]) & 15)) return NPGP_EUNSUPPORTED;
+    fb.A[i] = A[i], fb.P[i] = P[i], fb.flags[i] = static_cast<int*>(work[i]), fb.info[i] = info[i];
+  }
+  const int nb = (M + TB - 1) / TB;
+  NPGP_CUDA(cudaFuncSetAttribute(potrf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_SMEM));
+  for (int i = 0; i < n; ++i) {
+    NPGP_CUDA(cudaMemsetAsync(work[i], 0, (size_t)npgp_potrf_flow_workspace_bytes(M), stream));
+    NPGP_CUDA(cudaMemsetAsync(info[i], 0, sizeof(int), stream));
+  }
+  potrf_flow_kernel<<<n * nb * nb, CT, FLOW_SMEM, stream>>>(M, nb, fb, lda, ldp);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }

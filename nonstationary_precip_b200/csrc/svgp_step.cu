@@ -166,6 +166,61 @@ __global__ void svgp_outer_kernel(int M, int k, double alpha, const double* __re
   G[(long)r * M + c] = alpha * s;
 }
 
+// Skinny triangular products of the M x k (k <= 4) solves against the inverse factor P (lower): the generic DMMA GEMM spends
+// ~30 us of pure latency on them.  Y = P R: one warp per output row (fixed lane / shuffle order).
+template <int KP>
+__global__ void __launch_bounds__(256) svgp_tri_skinny_n_kernel(int M, const double* __restrict__ P, const double* __restrict__ R,
+                                                                double* __restrict__ Y) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= M) return;
+  double a[KP];
+#pragma unroll
+  for (int c = 0; c < KP; ++c) a[c] = 0.0;
+  for (int j = lane; j <= i; j += 32) {
+    const double pv = P[(long)i * M + j];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) a[c] = fma(pv, R[(long)j * KP + c], a[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < KP; ++c) {
+    const double t = warp_sum(a[c]);
+    if (lane == 0) Y[(long)i * KP + c] = t;
+  }
+}
+
+// W = P^T T: CTA = 32 columns j x 8 row groups; thread (g, j) adds rows i = j + g, j + g + 8, ... (P is read coalesced along j),
+// the eight groups are combined in index order through shared memory (bitwise reproducible; no atomics)
+template <int KP>
+__global__ void __launch_bounds__(256) svgp_tri_skinny_t_kernel(int M, const double* __restrict__ P, const double* __restrict__ T,
+                                                                double* __restrict__ W) {
+  __shared__ double sm[8][32][KP + 1];
+  const int jl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jl;
+  double a[KP];
+#pragma unroll
+  for (int c = 0; c < KP; ++c) a[c] = 0.0;
+  if (j < M) {
+    for (int i = blockIdx.x * 32 + g; i < M; i += 8) {
+      if (i < j) continue;
+      const double pv = P[(long)i * M + j];
+#pragma unroll
+      for (int c = 0; c < KP; ++c) a[c] = fma(pv, T[(long)i * KP + c], a[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < KP; ++c) sm[g][jl][c] = a[c];
+  __syncthreads();
+  if (g == 0 && j < M) {
+#pragma unroll
+    for (int c = 0; c < KP; ++c) {
+      double t = sm[0][jl][c];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += sm[k][jl][c];
+      W[(long)j * KP + c] = t;
+    }
+  }
+}
+
 struct AssembleArgs {
   int variant, M, d, nblk_kl, include_prior, B_local;
   long n_pad, n_params;
@@ -282,7 +337,7 @@ struct npgp_svgp_plan {
   double *zero_begin, *dfz_acc, *gZ, *dfx, *ds_acc, *dHx, *dD_acc, *dW, *dHz, *dummy_ell, *dalpha, *zero_end;
   double *beta4, *T4b, *R4b, *Gk, *dlog, *g_logell, *rv, *beta_v;
   int8_t *Ad, *Cd;
-  int *cexp, *skip_count, *skip_rows, *info, *flags0, *flags1;
+  int *cexp, *skip_count, *skip_rows, *info, *flags[8];  // flags[0]: Kzz, flags[1 + b]: prior-kernel factorisation b
   long flags_bytes, syrk_part_bytes, gwork_bytes;
 };
 
@@ -360,7 +415,7 @@ int svgp_layout(npgp_svgp_plan* p, void* workspace, long* bytes_out) {
   p->Ad = w.take<int8_t>(npgp_o8_digits_bytes(B, M, 128));
   p->Cd = w.take<int8_t>(npgp_o8_digits_bytes(M, M, 64));
   p->cexp = w.take<int>(M), p->skip_count = w.take<int>(4), p->skip_rows = w.take<int>(B), p->info = w.take<int>(8);
-  p->flags0 = w.take<int>(p->flags_bytes / 4 + 1), p->flags1 = w.take<int>(p->flags_bytes / 4 + 1);
+  for (int i = 0; i < 1 + nset; ++i) p->flags[i] = w.take<int>(p->flags_bytes / 4 + 1);
   *bytes_out = w.off + 256;
   return NPGP_OK;
 }
@@ -381,21 +436,35 @@ inline int fork_stream(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
 inline dim3 grid2(int M) { return dim3(ceil_div(M, 32), ceil_div(M, 8)); }
 const dim3 kBlk2(32, 8);
 
-// K^-1 rhs for rhs (M): P^T (P rhs)  (colwsum accumulates: out zeroed first)
-int solve_vec(npgp_svgp_plan* p, const double* Pm, const double* rhs, double* tmp, double* out, cudaStream_t st) {
-  const int M = p->c.M;
-  NPGP_TRY(npgp_gemv_n(M, M, Pm, M, rhs, tmp, st));
-  NPGP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * M, st));
-  NPGP_TRY(npgp_colwsum(M, M, Pm, M, tmp, out, st));
+template <int KP>
+int tri_skinny(int M, const double* Pm, const double* R, double* tmp, double* out, cudaStream_t st) {
+  svgp_tri_skinny_n_kernel<KP><<<ceil_div(M, 8), 256, 0, st>>>(M, Pm, R, tmp);
+  NPGP_LAUNCH_CHECK();
+  svgp_tri_skinny_t_kernel<KP><<<ceil_div(M, 32), 256, 0, st>>>(M, Pm, tmp, out);
+  NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
 
-// K^-1 rhs for rhs (M x k, leading dimension lds): padded to kp columns, two triangular GEMMs; result in out4 (M x kp)
+// out = P^T w (M): the transposed skinny product alone (u = P^T m)
+int tri_t_vec(int M, const double* Pm, const double* w, double* out, cudaStream_t st) {
+  svgp_tri_skinny_t_kernel<1><<<ceil_div(M, 32), 256, 0, st>>>(M, Pm, w, out);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// K^-1 rhs for rhs (M): P^T (P rhs), K = L L^T, P = L^-1
+int solve_vec(npgp_svgp_plan* p, const double* Pm, const double* rhs, double* tmp, double* out, cudaStream_t st) {
+  return tri_skinny<1>(p->c.M, Pm, rhs, tmp, out, st);
+}
+
+// K^-1 rhs for rhs (M x k, leading dimension lds): padded to kp columns; result in out4 (M x kp)
 int solve_cols(npgp_svgp_plan* p, const double* Pm, const double* rhs, long lds, int k, double* R4, double* T4, double* out4,
                cudaStream_t st) {
   const int M = p->c.M, kp = p->kp;
   svgp_pad_cols_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, k, kp, rhs, lds, R4);
   NPGP_LAUNCH_CHECK();
+  if (kp == 2) return tri_skinny<2>(M, Pm, R4, T4, out4, st);
+  if (kp == 4) return tri_skinny<4>(M, Pm, R4, T4, out4, st);
   NPGP_TRY(npgp_dgemm(0, 0, M, kp, M, 1.0, Pm, M, R4, kp, 0.0, T4, kp, 1, 0, 0, st));
   NPGP_TRY(npgp_dgemm(1, 0, M, kp, M, 1.0, Pm, M, T4, kp, 0.0, out4, kp, 2, 0, 0, st));
   return NPGP_OK;
@@ -522,10 +591,44 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
   else NPGP_TRY(npgp_gibbs_diag_fwd(d, M, M, Z, p->fz, Z, p->fz, s, p->Kzz, M, nullptr, nullptr, sd));
   svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, sd>>>(M, p->Kzz, M, c.jitter_zz + c.extra_jitter);
   NPGP_LAUNCH_CHECK();
-  NPGP_TRY(npgp_potrf_inv_flow(M, p->Kzz, M, p->P, M, p->flags0, p->flags_bytes, p->info, sd));
-  if (status) NPGP_TRY(npgp_status_update(status, p->info, nullptr, sd));
-  NPGP_CUDA(cudaMemsetAsync(p->u, 0, sizeof(double) * M, sd));
-  NPGP_TRY(npgp_colwsum(M, M, p->P, M, m, p->u, sd));
+  NPGP_CUDA(cudaEventRecord(p->ev[8], sd));  // Kzz is built
+
+  // ---- main stream: prior kernel(s) of the latent field at Z, then ALL factorisations of the step (Kzz and the prior
+  // kernels) in one batched dataflow launch
+  NPGP_TRY(stamp(p, 2 * SEC_FIELD, st));
+  const int nset = full ? 1 : d;
+  for (int b = 0; b < nset; ++b) {
+    double* lamb = p->lam_b + (long)b * d * M;
+    double* Kp = p->Kr + (long)b * MM;
+    svgp_bcast_rows_kernel<<<ceil_div(M, 256), 256, 0, st>>>(d, M, full ? c.row_lam : c.prior_lam + (long)b * d, lamb);
+    NPGP_LAUNCH_CHECK();
+    NPGP_TRY(npgp_gibbs_diag_fwd(d, M, M, Z, lamb, Z, lamb, full ? c.row_os : c.prior_os + b, Kp, M, nullptr, nullptr, st));
+    svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, Kp, M, full ? 1e-5 : 1e-4);
+    NPGP_LAUNCH_CHECK();
+  }
+  NPGP_CUDA(cudaStreamWaitEvent(st, p->ev[8], 0));
+  for (int first = 0; first < 1 + nset; first += 4) {  // matrix 0 = Kzz, 1 + b = prior kernel b; at most 4 per launch
+    double* As[4];
+    double* Ps[4];
+    void* Ws[4];
+    int* Is[4];
+    int n = 0;
+    for (int i = first; i < 1 + nset && n < 4; ++i, ++n) {
+      As[n] = i == 0 ? p->Kzz : p->Kr + (long)(i - 1) * MM;
+      Ps[n] = i == 0 ? p->P : p->Pr + (long)(i - 1) * MM;
+      Ws[n] = p->flags[i];
+      Is[n] = p->info + i;
+    }
+    NPGP_TRY(npgp_potrf_inv_flow_batch(n, M, As, M, Ps, M, Ws, p->flags_bytes, Is, st));
+    if (status)
+      for (int k = 0; k < n; ++k) NPGP_TRY(npgp_status_update(status, Is[k], nullptr, st));
+    if (first == 0) NPGP_CUDA(cudaEventRecord(p->ev[9], st));  // L, P of Kzz are ready
+  }
+
+  // ---- side stream: u = P^T m, C = P^T (Ls Ls^T - I) P and its digit planes
+  NPGP_CUDA(cudaStreamWaitEvent(sd, p->ev[9], 0));
+  NPGP_TRY(tri_t_vec(M, p->P, m, p->u, sd));  // u = P^T m
+  NPGP_CUDA(cudaEventRecord(p->ev[10], sd));   // all the K(X_B,Z) tile kernel needs from this chain; C is only needed by T = K C
   NPGP_CUDA(cudaStreamWaitEvent(sd, p->ev[2], 0));
   NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 1.0, p->E, M, p->P, M, 0.0, p->EP, M, 0, 1, 0, sd));
   NPGP_TRY(npgp_dgemm(1, 0, M, M, M, 1.0, p->P, M, p->EP, M, 0.0, p->C, M, 2, 0, 0, sd));
@@ -533,16 +636,8 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
   NPGP_TRY(stamp(p, 2 * SEC_ZZ + 1, sd));
   NPGP_CUDA(cudaEventRecord(p->ev[3], sd));
 
-  // ---- main stream: latent field at the rows (prior-kernel factorisations at Z, matrix-free interpolation)
-  NPGP_TRY(stamp(p, 2 * SEC_FIELD, st));
+  // ---- main stream: interpolation weights and the latent field at the rows (matrix free)
   if (full) {
-    svgp_bcast_rows_kernel<<<ceil_div(M, 256), 256, 0, st>>>(d, M, c.row_lam, p->lam_b);
-    NPGP_LAUNCH_CHECK();
-    NPGP_TRY(npgp_gibbs_diag_fwd(d, M, M, Z, p->lam_b, Z, p->lam_b, c.row_os, p->Kr, M, nullptr, nullptr, st));
-    svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, p->Kr, M, 1e-5);
-    NPGP_LAUNCH_CHECK();
-    NPGP_TRY(npgp_potrf_inv_flow(M, p->Kr, M, p->Pr, M, p->flags1, p->flags_bytes, p->info + 1, st));
-    if (status) NPGP_TRY(npgp_status_update(status, p->info + 1, nullptr, st));
     NPGP_TRY(solve_cols(p, p->Pr, F, d, d, p->R4, p->T4, p->W4, st));   // W = (K_row + 1e-5 I)^-1 H
     svgp_pad_cols_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, d, d, p->W4, p->kp, p->Wp);
     NPGP_LAUNCH_CHECK();
@@ -550,28 +645,20 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
     NPGP_TRY(npgp_sigma_from_h_fwd(d, B, p->Hx, Dm, p->fx, st));
   } else {
     for (int b = 0; b < d; ++b) {
-      double* lamb = p->lam_b + (long)b * d * M;
-      double* Kp = p->Kr + (long)b * MM;
-      double* Pb = p->Pr + (long)b * MM;
-      svgp_bcast_rows_kernel<<<ceil_div(M, 256), 256, 0, st>>>(d, M, c.prior_lam + (long)b * d, lamb);
-      NPGP_LAUNCH_CHECK();
-      NPGP_TRY(npgp_gibbs_diag_fwd(d, M, M, Z, lamb, Z, lamb, c.prior_os + b, Kp, M, nullptr, nullptr, st));
-      svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, Kp, M, 1e-4);
-      NPGP_LAUNCH_CHECK();
-      NPGP_TRY(npgp_potrf_inv_flow(M, Kp, M, Pb, M, p->flags1, p->flags_bytes, p->info + 1 + b, st));
-      if (status) NPGP_TRY(npgp_status_update(status, p->info + 1 + b, nullptr, st));
+      const double* Pb = p->Pr + (long)b * MM;
       svgp_sub_scalar_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, F + (long)b * M, c.prior_c + b, p->rhs + (long)b * M);
       NPGP_LAUNCH_CHECK();
       NPGP_TRY(solve_vec(p, Pb, p->rhs + (long)b * M, p->tmpv, p->alpha + (long)b * M, st));
       if (c.include_prior) {
-        svgp_lp_part_kernel<<<1, 256, 0, st>>>(M, p->rhs + (long)b * M, p->alpha + (long)b * M, Kp, p->lp_part + 2 * b);
+        svgp_lp_part_kernel<<<1, 256, 0, st>>>(M, p->rhs + (long)b * M, p->alpha + (long)b * M, p->Kr + (long)b * MM,
+                                               p->lp_part + 2 * b);
         NPGP_LAUNCH_CHECK();
       }
     }
     NPGP_TRY(npgp_rbf_matvec_fwd(d, d, 1, B, M, x, Z, c.prior_lam, c.prior_os, p->alpha, c.prior_c, 1, p->ell_x, st));
   }
   NPGP_TRY(stamp(p, 2 * SEC_FIELD + 1, st));
-  NPGP_CUDA(cudaStreamWaitEvent(st, p->ev[3], 0));
+  NPGP_CUDA(cudaStreamWaitEvent(st, p->ev[10], 0));
 
   // ---- data pass: K(X_B,Z) as digit planes (+ partial K u), T = K C with the row dot and K^T g_mu, E[log-lik]
   NPGP_TRY(stamp(p, 2 * SEC_KXZ, st));
@@ -581,6 +668,7 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
     NPGP_TRY(npgp_gibbs_diag_fwd_digits(d, B, M, x, p->ell_x, Z, p->fz, s, p->Ad, p->u, p->mu_part, B, st));
   NPGP_TRY(npgp_mu_gmu_parts(B, y, p->mu_part, p->nsplit, B, noise, 1.0 / c.B_global, p->mu, p->gmu0, st));
   NPGP_TRY(stamp(p, 2 * SEC_KXZ + 1, st));
+  NPGP_CUDA(cudaStreamWaitEvent(st, p->ev[3], 0));  // C and its digit planes (computed under the tile kernel above)
   NPGP_TRY(stamp(p, 2 * SEC_RQ, st));
   NPGP_TRY(npgp_o8_rowquad_digits(B, M, p->Ad, nullptr, s, p->Cd, p->cexp, nullptr, 0, p->T, M, p->q_part, B, p->gmu0,
                                   p->du_part, st));

@@ -411,6 +411,22 @@ def potrf_inv(A, overwrite=False, impl=None):
     return L, P, info
 
 
+def potrf_inv_batch(mats):
+    """Lower Cholesky factors and inverse factors of up to 4 SPD matrices of the same order in ONE dataflow launch
+    (npgp_potrf_inv_flow_batch).  Returns [(L, P, info), ...]; the inputs are not modified."""
+    import ctypes as C
+    n, M = len(mats), mats[0].shape[0]
+    Ls = [A.clone() for A in mats]
+    Ps = [torch.empty_like(A) for A in mats]
+    infos = [torch.zeros((), dtype=torch.int32, device=mats[0].device) for _ in mats]
+    nbytes = lib().npgp_potrf_flow_workspace_bytes(M)
+    works = [torch.empty(nbytes // 4 + 1, dtype=torch.int32, device=mats[0].device) for _ in mats]
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    check(lib().npgp_potrf_inv_flow_batch(n, M, arr(Ls), Ls[0].stride(0), arr(Ps), Ps[0].stride(0), arr(works), nbytes,
+                                          arr(infos), stream()), "npgp_potrf_inv_flow_batch")
+    return list(zip(Ls, Ps, infos))
+
+
 def colwsum(K, w=None, out=None):
     """out[j] (+)= sum_i w_i K[i,j]."""
     n, M = K.shape

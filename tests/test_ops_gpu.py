@@ -228,6 +228,31 @@ def test_potrf_reports_first_bad_pivot(ops, impl):
     assert int(info) == 131
 
 
+@pytest.mark.parametrize("n,M", [(2, 1024), (4, 1024), (3, 300), (4, 64)])
+def test_potrf_flow_batch(ops, n, M):
+    """All factorisations of a step (Kzz + the field prior's kernel matrices) in ONE interleaved dataflow launch."""
+    g = torch.Generator().manual_seed(7 * n + M)
+    mats = []
+    for k in range(n):
+        X = torch.rand(M, 3, generator=g) * 2 - 1
+        ell = torch.full((3, M), 0.25 + 0.05 * k)
+        mats.append((o.gibbs_diag_K(X, X, ell, ell) + 1e-6 * torch.eye(M)).cuda())
+    if n == 4:
+        mats[2] = mats[2].clone()
+        mats[2][M // 2, M // 2] = -1.0  # one failing matrix must not disturb the others
+    eye = torch.eye(M, device="cuda")
+    for _ in range(2):
+        outs = ops.potrf_inv_batch(mats)
+    for k, ((L, P, info), A) in enumerate(zip(outs, mats)):
+        if n == 4 and k == 2:
+            assert int(info) == M // 2 + 1
+            continue
+        assert int(info) == 0
+        assert rel(L @ L.T, A) < 1e-14 and (P @ L - eye).abs().max() < 1e-8
+        L1, P1, _ = ops.potrf_inv(A, impl="flow")
+        assert torch.equal(L, L1) and torch.equal(P, P1)  # same tile arithmetic as the single-matrix launch
+
+
 def test_potrf_flow_two_factorisations_on_two_streams(ops):
     """The SVGP step factors Kzz and the field prior's kernel matrix concurrently: two dataflow kernels sharing the SMs."""
     g = torch.Generator().manual_seed(5)

@@ -41,7 +41,7 @@ def test_c_step_matches_oracle_and_python_engine(variant, d, B, M):
     assert abs(loss_c.item() - loss_p.item()) < 1e-10 * abs(loss_p.item())
     for name in mp.g:
         assert rel(mc.g[name], mp.g[name]) < 1e-7, name  # FP64 atomics in both engines; the oracle bound above is the parity claim
-    assert rel(mc.last["mu"], mp.last["mu"]) < 1e-10  # (u = P^T m is accumulated with FP64 atomics in both engines)
+    assert rel(mc.last["mu"], mp.last["mu"]) < 1e-8  # (the engines solve K_row W = H with different kernels: cond(K_row) eps)
 
 
 @pytest.mark.parametrize("variant", ["full", "diag"])

@@ -49,3 +49,27 @@ for M in (512, 1024, 2048):
         for impl in ("flow", "steps"):
             ms, best = timeit(lambda: both(impl))
             print(json.dumps(dict(kernel="2 x potrf_inv[%s] on two streams" % impl, M=M, ms_median=round(ms, 4), ms_best=round(best, 4))), flush=True)
+
+# batched launch (round 2): n matrices in one interleaved dataflow kernel
+if __name__ == "__main__":
+    import json as _json
+    from nonstationary_precip_b200 import ops as _ops
+    for _n in (1, 2, 4):
+        _g = torch.Generator().manual_seed(_n)
+        _mats = []
+        for _ in range(_n):
+            _X = torch.rand(1024, 3, generator=_g, dtype=torch.float64) * 2 - 1
+            _mats.append((torch.exp(-((_X[:, None] - _X[None]) ** 2).sum(-1) / 0.18) + 1e-6 * torch.eye(1024, dtype=torch.float64)).cuda())
+        for _ in range(3):
+            _ops.potrf_inv_batch(_mats)
+        torch.cuda.synchronize()
+        _ts = []
+        for _ in range(10):
+            _a, _b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            _a.record()
+            _ops.potrf_inv_batch(_mats)
+            _b.record()
+            _b.synchronize()
+            _ts.append(_a.elapsed_time(_b))
+        print(_json.dumps({"kernel": "potrf_inv_flow_batch (incl. %d input copies and allocations)" % _n, "n": _n, "M": 1024,
+                           "ms_median": round(sorted(_ts)[5], 4), "ms_best": round(min(_ts), 4)}), flush=True)
