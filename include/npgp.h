@@ -326,6 +326,8 @@ int npgp_allreduce_f64_pair(void* comm, double* buf1, long n1, double* buf2, lon
  * memory; n_tile 256 = densest shape, 64 = the digit engine's tile; collector = A reuse hints) ---- */
 int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out, npgp_stream_t stream);
 int npgp_i8_peak_probe(int n_tile, int collector, int blocks, int reps, npgp_stream_t stream);
+/* the same for CTA pairs (tcgen05.mma.cta_group::2, 256 x n_tile x 32 per MMA; blocks even) */
+int npgp_i8_peak_probe_pair(int n_tile, int collector, int blocks, int reps, npgp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ _SIGS = {
     "npgp_potrf_inv_flow_batch": ([_i, _i, _p, _l, _p, _l, _p, _l, _p, _p], _i),
     "npgp_fp64_peak_probe": ([_i, _i, _i, _p, _p], _i),
     "npgp_i8_peak_probe": ([_i, _i, _i, _i, _p], _i),
+    "npgp_i8_peak_probe_pair": ([_i, _i, _i, _i, _p], _i),
     "npgp_set_gemm_config": ([_i], _i),
     "npgp_colwsum": ([_i, _i, _p, _l, _p, _p, _p], _i),
     "npgp_gemv_n": ([_i, _i, _p, _l, _p, _p, _p], _i),

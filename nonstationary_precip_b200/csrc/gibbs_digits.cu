@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(GD_ROWS) gibbs_full_fwd_digits_kernel(
       Sj[p] = S2[(long)j * P + p];
       scol[c][d + p] = Sj[p];
     }
-    scol[c][d + P] = sqrt(sqrt(sym_det<d>(Sj))) * s;
+    scol[c][d + P] = full_col_factor<d>(sym_det<d>(Sj)) * s;  // 2^(d/2) det(S_j)^(1/4) * outputscale
     scol[c][d + P + 1] = HAS_U ? u[j] : 0.0;
   }
   double xi[d], Si[P];

@@ -56,7 +56,7 @@ __device__ __forceinline__ void load_col_full(int n2, int j, const double* __res
 #pragma unroll
     for (int p = 0; p < P; ++p) S[p] = S2[(long)j * P + p];
   }
-  q = sqrt(sqrt(sym_det<d>(S)));
+  q = full_col_factor<d>(sym_det<d>(S));  // includes the 2^(d/2) of det(A)^(-1/2)
 }
 
 template <int d, bool HAS_U>
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel
   for (int c = 0; c < CPT; ++c) {
     load_col_full<d>(n2, jbase + c, x2, S2, z[c], Sj[c], qj[c], valid[c]);
     cv[c] = (g.colvec && valid[c]) ? g.colvec[jbase + c] : 0.0;
+    qj[c] *= s;  // K, and with it every g K below, carries the outputscale
   }
   double cW[CPT][P], cs0[CPT], cxz[CPT][d];
 #pragma unroll
@@ -151,7 +152,6 @@ __global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel
 #pragma unroll
     for (int k = 0; k < d; ++k) cxz[c][k] = 0.0;
   }
-  double acc_scale = 0.0;
   GPrefetch<CPT> gq(g, jbase, valid, vec_ok, row_begin, row_end);
 
   for (int i0 = row_begin; i0 < row_end; i0 += kTI) {
@@ -177,29 +177,29 @@ __global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         FullPair<d> pr;
-        gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[c], Sj[c], qj[c], jit2, sexp, &pr);
-        const double gk0 = valid[c] ? gv[c] * pr.k : 0.0;
-        acc_scale += gk0;
-        const double gk = gk0 * s;
+        gibbs_full_eval<d>(sx[r], sS[r], sq[r], z[c], Sj[c], qj[c], jit2, sexp, &pr);  // qj carries the outputscale
+        const double gk = valid[c] ? gv[c] * pr.k : 0.0;
         rs0 += gk;
         cs0[c] += gk;
-        const double hgk = 0.5 * gk;
-        // dlogK/dSigma (pair part, same for both sides) = 0.5 w w^T - 0.25 A^-1
+        // dlogK/dSigma (pair part, same for both sides) = 0.5 w w^T - 0.25 A^-1 = 0.5 w w^T - hr2 adj(At)
+        const double c2 = -gk * pr.hr2;
+        double t[d];  // 0.5 gk w: also the input gradient, 2 gk w = 4 t (the factor is applied once, after the loops)
+#pragma unroll
+        for (int a = 0; a < d; ++a) t[a] = (0.5 * gk) * pr.w[a];
 #pragma unroll
         for (int a = 0; a < d; ++a)
 #pragma unroll
           for (int b = a; b < d; ++b) {
             const int p = sym_idx(d, a, b);
-            const double w = fma(hgk * pr.w[a], pr.w[b], -gk * pr.hA[p]);
+            const double w = fma(t[a], pr.w[b], c2 * pr.adjA[p]);
             rW[p] += w;
             cW[c][p] += w;
           }
         if (DX1 || DX2) {
 #pragma unroll
           for (int k = 0; k < d; ++k) {
-            const double xz = 2.0 * gk * pr.w[k];
-            if (DX1) rxz[k] += xz;
-            if (DX2) cxz[c][k] += xz;
+            if (DX1) rxz[k] += t[k];
+            if (DX2) cxz[c][k] += t[k];
           }
         }
       }
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel
 #pragma unroll
         for (int p = 0; p < P; ++p) atomicAdd(&d_S1[(long)i * P + p], f * adj[p]);
       } else if (DX1) {
-        atomicAdd(&d_x1[(long)i * d + (comp - P - 1)], -v);
+        atomicAdd(&d_x1[(long)i * d + (comp - P - 1)], -4.0 * v);
       }
     }
   }
@@ -244,11 +244,14 @@ __global__ void __launch_bounds__(kNT, NPGP_FULL_BWD_MINB) gibbs_full_bwd_kernel
     for (int p = 0; p < P; ++p) atomicAdd(&d_S2[(long)j * P + p], fma(f, adj[p], cW[c][p]));
     if (DX2) {
 #pragma unroll
-      for (int k = 0; k < d; ++k) atomicAdd(&d_x2[(long)j * d + k], cxz[c][k]);
+      for (int k = 0; k < d; ++k) atomicAdd(&d_x2[(long)j * d + k], 4.0 * cxz[c][k]);
     }
   }
-  if (d_scale) {
-    const double t = block_sum(acc_scale, red);
+  if (d_scale) {  // dL/ds = sum_ij G_ij K_ij / s: the column sums of g K (K carries s)
+    double acc_scale = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc_scale += valid[c] ? cs0[c] : 0.0;
+    const double t = block_sum(acc_scale / s, red);
     if (threadIdx.x == 0) atomicAdd(d_scale, t);
   }
 }

@@ -186,47 +186,71 @@ NPGP_HD int sym_idx(int d, int k, int l) {  // k <= l
   return k * d - (k * (k - 1)) / 2 + (l - k);
 }
 
+// adjugate / determinant of Bt = At + lam I from those of At, d = 3: the off-diagonal cofactors differ by -lam * At_p (one
+// FMA instead of a product and an FMA); the diagonal ones are recomputed from the shifted diagonal (same cost either way)
+template <int d>
+NPGP_HD void sym_adj_det_shifted(const double* At, const double* adjA, double lam, double* adjB, double& detB);
+template <>
+NPGP_HD void sym_adj_det_shifted<2>(const double* At, const double* adjA, double lam, double* adjB, double& detB) {
+  (void)adjA;
+  const double b0 = At[0] + lam, b2 = At[2] + lam;
+  adjB[0] = b2;
+  adjB[1] = -At[1];
+  adjB[2] = b0;
+  detB = fma(b0, b2, -At[1] * At[1]);
+}
+template <>
+NPGP_HD void sym_adj_det_shifted<3>(const double* At, const double* adjA, double lam, double* adjB, double& detB) {
+  const double b0 = At[0] + lam, b3 = At[3] + lam, b5 = At[5] + lam;
+  adjB[0] = fma(b3, b5, -At[4] * At[4]);
+  adjB[1] = fma(-lam, At[1], adjA[1]);
+  adjB[2] = fma(-lam, At[2], adjA[2]);
+  adjB[3] = fma(b0, b5, -At[2] * At[2]);
+  adjB[4] = fma(-lam, At[4], adjA[4]);
+  adjB[5] = fma(b0, b3, -At[1] * At[1]);
+  detB = fma(b0, adjB[0], fma(At[1], adjB[1], At[2] * adjB[2]));
+}
+
 template <int d>
 struct FullPair {
-  double k;                  // unscaled kernel value
+  double k;                  // kernel value (scaled as qj is)
   double w[d];               // (A + eps I)^-1 delta
-  double hA[sym_size(d)];    // 0.5 * adj(At)/det(At) = 0.25 * A^-1
+  double adjA[sym_size(d)];  // adj(At), At = S_i + S_j
+  double hr2;                // 0.5 / det(At): 0.25 A^-1 = hr2 * adjA
 };
 
-// xi, Si (packed), qi = det(Si)^(1/4); likewise column point.  jit2 = 2 * jitter.
+// xi, Si (packed), qi = det(Si)^(1/4); column point zj, Sj and qj = 2^(d/2) det(Sj)^(1/4) [* outputscale]: the constant of
+// det(A)^(-1/2) = 2^(d/2) rsqrt(det At) is folded into the column factor by the callers (full_col_factor).  jit2 = 2 * jitter.
+template <int d>
+NPGP_HD double full_col_factor(double det_Sj) {
+  return ((d == 2) ? 2.0 : 2.8284271247461900976) * sqrt(sqrt(det_Sj));
+}
+
 template <int d>
 NPGP_HD double gibbs_full_eval(const double* xi, const double* Si, double qi, const double* zj, const double* Sj,
                                double qj, double jit2, const double* etab, FullPair<d>* out = nullptr) {
   constexpr int P = sym_size(d);
-  double At[P], Bt[P], adjA[P], adjB[P], detA, detB, dl[d], v[d];
+  double At[P], adjA[P], adjB[P], detA, detB, dl[d], v[d];
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    At[p] = Si[p] + Sj[p];
-    Bt[p] = At[p];
-  }
+  for (int p = 0; p < P; ++p) At[p] = Si[p] + Sj[p];
 #pragma unroll
-  for (int k = 0; k < d; ++k) {
-    Bt[sym_idx(d, k, k)] += jit2;
-    dl[k] = xi[k] - zj[k];
-  }
+  for (int k = 0; k < d; ++k) dl[k] = xi[k] - zj[k];
   sym_adj_det<d>(At, adjA, detA);
-  sym_adj_det<d>(Bt, adjB, detB);
+  sym_adj_det_shifted<d>(At, adjA, jit2, adjB, detB);
   sym_matvec<d>(adjB, dl, v);
   double dv = 0.0;
 #pragma unroll
   for (int k = 0; k < d; ++k) dv = fma(dl[k], v[k], dv);
-  const double idetB2 = 2.0 * fast_rcp(detB);
+  const double nidetB2 = -2.0 * fast_rcp(detB);  // -(A + eps I)^-1 = nidetB2 * adj(Bt)
   const double r = fast_rsqrt(detA);
-  // det(A)^(-1/2) = 2^(d/2) rsqrt(det At)
-  const double pow2 = (d == 2) ? 2.0 : 2.8284271247461900976;
-  const double k = (qi * qj) * (pow2 * r) * exp_neg(-dv * idetB2, etab);
+  const double k = (qi * qj) * r * exp_neg(dv * nidetB2, etab);
   if (out) {
     out->k = k;
-    const double hr2 = 0.5 * r * r;
+    out->hr2 = 0.5 * r * r;
 #pragma unroll
-    for (int a = 0; a < d; ++a) out->w[a] = v[a] * idetB2;
+    for (int a = 0; a < d; ++a) out->w[a] = -v[a] * nidetB2;
 #pragma unroll
-    for (int p = 0; p < P; ++p) out->hA[p] = adjA[p] * hr2;
+    for (int p = 0; p < P; ++p) out->adjA[p] = adjA[p];
   }
   return k;
 }

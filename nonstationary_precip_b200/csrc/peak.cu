@@ -120,6 +120,95 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int reps) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// The same measurement for a CTA PAIR (cta_group::2): one MMA covers 256 x N x 32 -- 128 rows of A from each CTA's shared
+// memory, N/2 rows of B from each -- so per SM the B traffic is halved.  Both CTAs allocate TMEM, the leader issues,
+// one multicast commit signals both.
+#define PK_MMA2(NAME, COLL)                                                                                         \
+  __device__ __forceinline__ void NAME(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc) {                      \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"                                                  \
+                 "tcgen05.mma.cta_group::2.kind::i8" COLL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),                  \
+                 "l"(da), "l"(db), "r"(idesc)                                                                       \
+                 : "memory");                                                                                       \
+  }
+PK_MMA2(pk2_mma, "")
+PK_MMA2(pk2_mma_fill, ".collector::a::fill")
+PK_MMA2(pk2_mma_use, ".collector::a::use")
+PK_MMA2(pk2_mma_last, ".collector::a::lastuse")
+
+__device__ __forceinline__ void pk_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int N, bool COLL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) i8_peak2_kernel(int reps) {
+  extern __shared__ __align__(1024) uint8_t pk_sm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  constexpr int NB = 8, NH = N / 2;     // this CTA holds half of the rows of every B tile
+  uint8_t* sA = pk_sm;                  // 128 x 32 bytes (this CTA's half of the 256 rows)
+  uint8_t* sB = pk_sm + 4096;           // NB x (N/2 x 32 bytes)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int e = tid; e < 4096 + NB * NH * 32; e += 128) pk_sm[e] = (uint8_t)(e * 2654435761u >> 13);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pk_smem(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pk_smem(&tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  pk_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  if (warp == 0) {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n" : "=r"(pred));
+    if (rank == 0) {
+      const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint64_t da = pk_desc(pk_smem(sA), 128 * 16, 128);
+      uint64_t db[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) db[b] = pk_desc(pk_smem(sB + b * NH * 32), NH * 16, 128);
+      constexpr int NACC = 512 / N;
+      for (int r = 0; r < reps; ++r) {
+        if (pred) {
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const uint32_t d = tmem + (uint32_t)((b % NACC) * N);
+            if (!COLL) pk2_mma(d, da, db[b], idesc);
+            else if (b == 0) pk2_mma_fill(d, da, db[b], idesc);
+            else if (b == NB - 1) pk2_mma_last(d, da, db[b], idesc);
+            else pk2_mma_use(d, da, db[b], idesc);
+          }
+        }
+        __syncwarp();
+      }
+      if (pred)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         pk_smem(&bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+      __syncwarp();
+    }
+    uint32_t done = 0;
+    long spins = 0;
+    while (!done && ++spins < (1L << 26))  // bounded: a wrong guess about the pair protocol must not hang the GPU
+      asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                   : "=r"(done)
+                   : "r"(pk_smem(&bar)), "r"(0u)
+                   : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  pk_cluster_sync();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 }  // namespace npgp
 
 // int8 tensor-core probe: `blocks` CTAs x reps x 8 MMAs of 128 x n_tile x 32; int8 operations launched =
@@ -145,6 +234,23 @@ extern "C" int npgp_fp64_peak_probe(int mode, int blocks, int iters, double* out
   if (!out || blocks <= 0 || iters <= 0) return NPGP_EINVAL;
   if (mode == 0) npgp::dfma_peak_kernel<<<blocks, 256, 0, stream>>>(iters, 1.0, out);
   else npgp::dmma_peak_kernel<<<blocks, 256, 0, stream>>>(iters, 1.0, out);
+  NPGP_LAUNCH_CHECK();
+  return NPGP_OK;
+}
+
+// CTA-pair variant of npgp_i8_peak_probe: blocks (even) CTAs in clusters of 2, every pair issues reps x 8 MMAs of
+// 256 x n_tile x 32 (tcgen05.mma.cta_group::2); int8 operations = (blocks / 2) * reps * 8 * 2 * 256 * n_tile * 32.
+extern "C" int npgp_i8_peak_probe_pair(int n_tile, int collector, int blocks, int reps, cudaStream_t stream) {
+  if (blocks <= 0 || (blocks & 1) || reps <= 0 || (n_tile != 64 && n_tile != 256)) return NPGP_EINVAL;
+  const int smem = 4096 + 8 * (n_tile / 2) * 32;
+#define NPGP_PK2(NT, CL)                                                                                               \
+  do {                                                                                                                \
+    NPGP_CUDA(cudaFuncSetAttribute(npgp::i8_peak2_kernel<NT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    npgp::i8_peak2_kernel<NT, CL><<<blocks, 128, smem, stream>>>(reps);                                                \
+  } while (0)
+  if (n_tile == 256) { if (collector) NPGP_PK2(256, true); else NPGP_PK2(256, false); }
+  else { if (collector) NPGP_PK2(64, true); else NPGP_PK2(64, false); }
+#undef NPGP_PK2
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
