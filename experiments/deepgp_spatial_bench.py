@@ -73,8 +73,8 @@ def run_state(random_state, dataset, args, device):
     train_s = time.perf_counter() - t0
     test_loader = DataLoader(TensorDataset(test_x, test_y), batch_size=args.batch_size)
     model.eval()
-    with torch.no_grad(), m.num_likelihood_samples(args.num_samples):
-        pred_y, y_means, y_var, test_lls = model.predict(test_loader)
+    with torch.no_grad():  # as the reference (:96-100): prediction runs outside the settings context, i.e. with the default
+        pred_y, y_means, y_var, test_lls = model.predict(test_loader)  # of 10 likelihood samples, not the training count
     # RMSE on the sample-averaged predictive mean; NLPD from the per-point log marginals that `predict` returns (the
     # DSVI layers here carry marginals only, so the script's joint `pred_y.log_prob` (:112) is replaced by their sum)
     rmse_test = float(rmse(y_means.mean(0) if y_means.dim() > 1 else y_means, test_y, stdy))
