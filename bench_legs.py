@@ -106,7 +106,7 @@ def leg_c4(rank, world, dev, allmax, all_reduce):
         k[0] += 1
         return loss.detach()
 
-    ms, loss = _timed(step, warm=1, iters=2)
+    ms, loss = _timed(step, warm=2, iters=3)  # (the first two steps allocate the 7.5 GB digit workspace of the int8 path)
     ms = allmax(ms)
     # work actually executed per step (T = K C is cached between forward and backward): 4 (S + 2) B M^2
     out = {"what": "c4: 2-layer DGP, DSVI, B=%d, M=%d per layer, S=%d samples sharded over %d rank(s), fp64" % (B, M, S, world),
