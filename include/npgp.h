@@ -175,6 +175,23 @@ int npgp_dsvi_sample_bwd(long n, const double* var, const double* eps, const dou
 int npgp_gauss_ell_batched(int S, int n, const double* y, const double* mu, const double* var, const double* noise,
                            double wscale, double* sums, double* sq, double* gmu, double* gvar, npgp_stream_t stream);
 
+/* One output dimension of a deep-GP layer (csrc/dsvi_layer.cu): the whitened-SVGP marginals at the rows X for an RBF-ARD * Scale
+ * kernel (reference models/dgps.py:15-46 through GPyTorch's VariationalStrategy / DeepGPLayer.__call__) and their analytic
+ * backward.  X (n,d): S x B samples of the previous layer (or the B data rows); Z (M,d); ls (d), os (1): constrained
+ * lengthscales / outputscale on the device; m (M), Ls (M,M, lower part used).  fwd: mean = K u (the caller adds the mean
+ * function), var = max(os + add_var + rowdot(K C, K), min_var), *info = the Cholesky's code.  bwd: all outputs OVERWRITTEN
+ * (dX (n,d) may be NULL; dLs lower triangle).  work: npgp_dsvi_layer_workspace_bytes(n, M, d) bytes, 256-byte aligned, passed
+ * unchanged from fwd to bwd (it carries K, T = K C and the Z-side factors).  M even, d <= 6.  T = K C and, when all
+ * variance seeds are equal (decided on the device), K^T diag(dvar) K run on the int8 tensor cores. */
+long npgp_dsvi_layer_workspace_bytes(int n, int M, int d);
+int npgp_dsvi_layer_fwd(int n, int M, int d, const double* X, const double* Z, const double* ls, const double* os,
+                        const double* m, const double* Ls, double jitter, double add_var, double min_var, double* mean,
+                        double* var, int* info, void* work, long work_bytes, npgp_stream_t stream);
+int npgp_dsvi_layer_bwd(int n, int M, int d, const double* X, const double* Z, const double* ls, const double* os,
+                        const double* m, const double* var, double min_var, const double* dmean, const double* dvar,
+                        double* dX, double* dZ, double* dls, double* dos, double* dm, double* dLs, void* work, long work_bytes,
+                        npgp_stream_t stream);
+
 /* ---- temporal kernel of the spatio-temporal model (models/spatio_temporal_models.py:42):
  * K[i,j] = s exp(-0.5 tau^2/l_r^2) exp(-2 sin^2(pi |tau|/p)/l_p), tau = t1[i] - t2[j]; hyp (device) = [l_r, l_p, p, s].
  * Backward: out4 += dL/d[l_r, l_p, p, s]; dt2 (n2, may be NULL) += dL/dt2. */

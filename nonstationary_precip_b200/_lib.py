@@ -91,6 +91,9 @@ _SIGS = {
     "npgp_dsvi_sample": ([_l, _p, _p, _p, C.c_ulonglong, C.c_ulonglong, _p, _p, _p], _i),
     "npgp_dsvi_sample_bwd": ([_l, _p, _p, _p, _p, _p, _p], _i),
     "npgp_gauss_ell_batched": ([_i, _i, _p, _p, _p, _p, _d, _p, _p, _p, _p, _p], _i),
+    "npgp_dsvi_layer_workspace_bytes": ([_i, _i, _i], _l),
+    "npgp_dsvi_layer_fwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _d, _p, _p, _p, _p, _l, _p], _i),
+    "npgp_dsvi_layer_bwd": ([_i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p], _i),
     "npgp_svgp_theta_size": ([_p], _l),
     "npgp_svgp_workspace_bytes": ([_p], _l),
     "npgp_svgp_plan_create": ([_p, _p, _p, _l], _i),

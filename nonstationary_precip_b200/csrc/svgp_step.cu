@@ -24,6 +24,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "svgp_glue.cuh"
 #include "../../include/npgp.h"
 
 namespace npgp {
@@ -42,24 +43,6 @@ __global__ void svgp_scalars_kernel(const double* __restrict__ raw_os, const dou
     scal[2] = sigmoid_t(*raw_os);
     scal[3] = sigmoid_t(*raw_noise);
   }
-}
-
-// dst = tril(src) (M x M, contiguous)
-__global__ void svgp_tril_copy_kernel(int M, const double* __restrict__ src, double* __restrict__ dst) {
-  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
-  if (r < M && c < M) dst[(long)r * M + c] = (c <= r) ? src[(long)r * M + c] : 0.0;
-}
-
-__global__ void svgp_add_diag_kernel(int M, double* __restrict__ A, long lda, double v) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i < M) A[(long)i * lda + i] += v;
-}
-
-// out (d x M): out[k][j] = lam[k]
-__global__ void svgp_bcast_rows_kernel(int d, int M, const double* __restrict__ lam, double* __restrict__ out) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j < M)
-    for (int k = 0; k < d; ++k) out[(long)k * M + j] = lam[k];
 }
 
 // dst (M x kp, zero padded) <- src (M x k, leading dimension lds) [- sub_b]
@@ -132,30 +115,6 @@ __global__ void svgp_grad_m_ls_kernel(int M, const double* __restrict__ dLs, con
   if (c == 0) g_m[r] = -(dm[r] - rep_over_N * m[r]);
 }
 
-// X <- -Phi(X + m dm^T): lower triangle, diagonal halved, upper zeroed
-__global__ void svgp_addr_phi_kernel(int M, double* __restrict__ X, const double* __restrict__ m, const double* __restrict__ dm) {
-  const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
-  if (r >= M || c >= M) return;
-  double* p = X + (long)r * M + c;
-  const double v = *p + m[r] * dm[c];
-  *p = (c < r) ? -v : ((c == r) ? -0.5 * v : 0.0);
-}
-
-// out = 0.5 (A + A^T)
-__global__ void svgp_sym_avg_kernel(int M, const double* __restrict__ A, double* __restrict__ out) {
-  __shared__ double tile[32][33];
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
-  for (int k = threadIdx.y; k < 32; k += 8) {
-    const int r = bx + k, c = by + threadIdx.x;  // transposed block
-    tile[k][threadIdx.x] = (r < M && c < M) ? A[(long)r * M + c] : 0.0;
-  }
-  __syncthreads();
-  for (int k = threadIdx.y; k < 32; k += 8) {
-    const int r = by + k, c = bx + threadIdx.x;
-    if (r < M && c < M) out[(long)r * M + c] = 0.5 * (A[(long)r * M + c] + tile[threadIdx.x][k]);
-  }
-}
-
 // Gk[i][j] = alpha * sum_c a[i*lda + c] b[j*ldb + c], c < k  (+ beta_old * Gk)
 __global__ void svgp_outer_kernel(int M, int k, double alpha, const double* __restrict__ a, long lda, const double* __restrict__ b,
                                   long ldb, double* __restrict__ G) {
@@ -164,61 +123,6 @@ __global__ void svgp_outer_kernel(int M, int k, double alpha, const double* __re
   double s = 0.0;
   for (int t = 0; t < k; ++t) s = fma(a[(long)r * lda + t], b[(long)c * ldb + t], s);
   G[(long)r * M + c] = alpha * s;
-}
-
-// Skinny triangular products of the M x k (k <= 4) solves against the inverse factor P (lower): the generic DMMA GEMM spends
-// ~30 us of pure latency on them.  Y = P R: one warp per output row (fixed lane / shuffle order).
-template <int KP>
-__global__ void __launch_bounds__(256) svgp_tri_skinny_n_kernel(int M, const double* __restrict__ P, const double* __restrict__ R,
-                                                                double* __restrict__ Y) {
-  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= M) return;
-  double a[KP];
-#pragma unroll
-  for (int c = 0; c < KP; ++c) a[c] = 0.0;
-  for (int j = lane; j <= i; j += 32) {
-    const double pv = P[(long)i * M + j];
-#pragma unroll
-    for (int c = 0; c < KP; ++c) a[c] = fma(pv, R[(long)j * KP + c], a[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < KP; ++c) {
-    const double t = warp_sum(a[c]);
-    if (lane == 0) Y[(long)i * KP + c] = t;
-  }
-}
-
-// W = P^T T: CTA = 32 columns j x 8 row groups; thread (g, j) adds rows i = j + g, j + g + 8, ... (P is read coalesced along j),
-// the eight groups are combined in index order through shared memory (bitwise reproducible; no atomics)
-template <int KP>
-__global__ void __launch_bounds__(256) svgp_tri_skinny_t_kernel(int M, const double* __restrict__ P, const double* __restrict__ T,
-                                                                double* __restrict__ W) {
-  __shared__ double sm[8][32][KP + 1];
-  const int jl = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + jl;
-  double a[KP];
-#pragma unroll
-  for (int c = 0; c < KP; ++c) a[c] = 0.0;
-  if (j < M) {
-    for (int i = blockIdx.x * 32 + g; i < M; i += 8) {
-      if (i < j) continue;
-      const double pv = P[(long)i * M + j];
-#pragma unroll
-      for (int c = 0; c < KP; ++c) a[c] = fma(pv, T[(long)i * KP + c], a[c]);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < KP; ++c) sm[g][jl][c] = a[c];
-  __syncthreads();
-  if (g == 0 && j < M) {
-#pragma unroll
-    for (int c = 0; c < KP; ++c) {
-      double t = sm[0][jl][c];
-#pragma unroll
-      for (int k = 1; k < 8; ++k) t += sm[k][jl][c];
-      W[(long)j * KP + c] = t;
-    }
-  }
 }
 
 struct AssembleArgs {

@@ -21,6 +21,7 @@ from .. import ops
 from ..gp_base import ConstantMean, ExactGP, GaussianLikelihood, LinearMean, Module, MultivariateNormal, RBFKernel, ScaleKernel
 
 num_output_dims = 2
+USE_C_LAYER = True  # route every layer output through npgp_dsvi_layer_fwd / _bwd (False: the kernel-by-kernel composition)
 
 
 class num_likelihood_samples:
@@ -148,6 +149,21 @@ class DeepGPLayer(Module):
         ls = (ls[o] if batched else ls).reshape(-1)
         os = (os[o] if batched else os).reshape(())
         M = Z.shape[0]
+        mean = var = None
+        if (USE_C_LAYER and X.is_cuda and X.dtype == torch.float64 and M % 2 == 0 and ls.numel() == X.shape[1]
+                and X.shape[1] <= 6):
+            # the whole layer output, forward and analytic backward, as one C call each (csrc/dsvi_layer.cu)
+            raw_Ls = vd.chol_variational_covar[o] if batched else vd.chol_variational_covar
+            mean, var, info = ops.dsvi_layer(X, Z, ls, os, m, raw_Ls, vs.jitter_val)
+            if int(info) != 0:  # psd_safe_cholesky's ladder lives in the composed path below
+                mean = var = None
+        if mean is not None:
+            if isinstance(self.mean_module, LinearMean):
+                mean = mean + self.mean_module(X)
+            else:
+                c = self.mean_module.constant
+                mean = mean + (c[o] if batched else c).reshape(())
+            return mean, var
         eye = torch.eye(M, dtype=X.dtype, device=X.device)
         Kzz = F.rbf_ard(Z, Z, ls, os) + vs.jitter_val * eye
         _, P = F.psd_safe_chol_inv(Kzz)

@@ -613,6 +613,54 @@ class DsviSampleFn(torch.autograd.Function):
         return dmu, dvar, None, None, None
 
 
+class DsviLayerFn(torch.autograd.Function):
+    """(mean = K u, var, info) of one output dimension of a whitened-SVGP deep-GP layer with an RBF-ARD * Scale kernel, forward
+    and analytic backward each ONE C call (csrc/dsvi_layer.cu: npgp_dsvi_layer_fwd / _bwd).  K, T = K C and the Z-side factors
+    travel from forward to backward in the call's workspace."""
+
+    @staticmethod
+    def forward(ctx, X, Z, ls, os, m, Ls, jitter):
+        Xc, Zc, lsc, osc, mc, Lsc = (t.detach().contiguous() for t in (X, Z, ls.reshape(-1), os.reshape(1), m, Ls))
+        n, d = Xc.shape
+        M = Zc.shape[0]
+        nbytes = lib().npgp_dsvi_layer_workspace_bytes(n, M, d)
+        if nbytes < 0:
+            raise _lib.NpgpError("npgp_dsvi_layer: unsupported shape n=%d M=%d d=%d" % (n, M, d))
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=Xc.device)
+        off = (-ws.data_ptr()) % 256
+        mean = torch.empty(n, dtype=torch.float64, device=Xc.device)
+        var = torch.empty_like(mean)
+        info = torch.zeros((), dtype=torch.int32, device=Xc.device)
+        check(lib().npgp_dsvi_layer_fwd(n, M, d, ptr(Xc), ptr(Zc), ptr(lsc), ptr(osc), ptr(mc), ptr(Lsc), float(jitter), 1e-4, 1e-6,
+                                        ptr(mean), ptr(var), ptr(info), ws.data_ptr() + off, nbytes, stream()),
+              "npgp_dsvi_layer_fwd")
+        ctx.save_for_backward(Xc, Zc, lsc, osc, mc, var)
+        ctx.ws, ctx.off, ctx.nbytes, ctx.shapes = ws, off, nbytes, (ls.shape, os.shape)
+        ctx.mark_non_differentiable(info)
+        return mean, var, info
+
+    @staticmethod
+    def backward(ctx, dmean, dvar, _):
+        Xc, Zc, lsc, osc, mc, var = ctx.saved_tensors
+        n, d = Xc.shape
+        M = Zc.shape[0]
+        z = lambda *s: torch.empty(*s, dtype=torch.float64, device=Xc.device)
+        dmean = dmean.contiguous() if dmean is not None else torch.zeros_like(var)
+        dvar = dvar.contiguous() if dvar is not None else torch.zeros_like(var)
+        dX = z(n, d) if ctx.needs_input_grad[0] else None
+        dZ, dls, dos, dm, dLs = z(M, d), z(d), z(1), z(M), z(M, M)
+        check(lib().npgp_dsvi_layer_bwd(n, M, d, ptr(Xc), ptr(Zc), ptr(lsc), ptr(osc), ptr(mc), ptr(var), 1e-6, ptr(dmean),
+                                        ptr(dvar), ptr(dX), ptr(dZ), ptr(dls), ptr(dos), ptr(dm), ptr(dLs),
+                                        ctx.ws.data_ptr() + ctx.off, ctx.nbytes, stream()), "npgp_dsvi_layer_bwd")
+        ctx.ws = None  # K and T (2 x n x M doubles) are released here
+        ls_shape, os_shape = ctx.shapes
+        return dX, dZ, dls.reshape(ls_shape), dos.reshape(os_shape), dm, dLs, None
+
+
+def dsvi_layer(X, Z, ls, os, m, Ls, jitter=1e-6):
+    return DsviLayerFn.apply(X, Z, ls, os, m, Ls, jitter)
+
+
 class GaussEllBatchedFn(torch.autograd.Function):
     """sums[s] = sum_i E_q log N(y_i | f_si, noise) for mu, var of shape (S, n); gradients to mu, var and noise."""
 

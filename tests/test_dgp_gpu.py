@@ -27,11 +27,16 @@ def layer_dict(layer, requires_grad=True):
     return d
 
 
-@pytest.mark.parametrize("num_layers", [1, 2])
-def test_dgp_elbo_and_gradients_match_oracle(num_layers):
+@pytest.mark.parametrize("c_layer", [True, False])
+@pytest.mark.parametrize("num_layers,B,M,S", [(1, 300, 24, 4), (2, 300, 24, 4), (1, 2048, 128, 4)])
+def test_dgp_elbo_and_gradients_match_oracle(num_layers, B, M, S, c_layer, monkeypatch):
+    """c_layer: every layer output through npgp_dsvi_layer_fwd / _bwd (one C call each) or through the kernel-by-kernel
+    composition.  (1, 2048, 128, 4): the last layer sees S * B = 8192 rows of width 128 -- T = K C and the equal-weights
+    K^T diag(dvar) K of its backward run on the int8 tensor cores."""
     from nonstationary_precip_b200.models import dgps
+    monkeypatch.setattr(dgps, "USE_C_LAYER", c_layer)
     torch.manual_seed(5)
-    B, d, M, S, N = 300, 2, 24, 4, 1200
+    d, N = 2, 4 * B
     g = torch.Generator().manual_seed(6)
     x = torch.rand(B, d, generator=g) * 2 - 1
     y = torch.sin(3 * x[:, 0]) + 0.1 * torch.randn(B, generator=g)
