@@ -630,13 +630,18 @@ class SVGPGibbs:
         return self.grad[-2]
 
     # ---- CUDA-graph execution: the ~250 launches of a step are captured once and replayed ---------------------------
-    def capture(self, B_local: int, world_size: int = 1, B_global: Optional[int] = None, lr: float = 0.01, all_reduce=None):
+    def capture(self, B_local: int, world_size: int = 1, B_global: Optional[int] = None, lr: float = 0.01, all_reduce=None,
+                buffers: int = 1):
         """Capture the whole step for minibatches of B_local rows: loss_and_grad, the all-reduce of the flat gradient
         (`all_reduce(self.grad)`, e.g. an NCCL all-reduce -- NCCL collectives are capturable) and the Adam update, so a
         replay is one graph launch on every rank.  Without `all_reduce` and world_size > 1 the collective and Adam run
-        after the replayed graph (train_step_graph(all_reduce=...))."""
+        after the replayed graph (train_step_graph(all_reduce=...)).
+        buffers = 2: two graphs over two static input buffers, used alternately, so that the host-to-device copy of the next
+        minibatch (on a copy stream) runs under the current step (train_step_graph_async / loss_result)."""
         f64 = dict(dtype=torch.float64, device=self.dev)
-        self._gx, self._gy = torch.zeros(B_local, self.d, **f64), torch.zeros(B_local, **f64)
+        self._gxs = [torch.zeros(B_local, self.d, **f64) for _ in range(buffers)]
+        self._gys = [torch.zeros(B_local, **f64) for _ in range(buffers)]
+        self._gx, self._gy = self._gxs[0], self._gys[0]
         self._g_world, self._g_lr = world_size, lr
         self._g_fused = world_size == 1 or all_reduce is not None
         snap = [t.clone() for t in (self.theta, self.adam_m, self.adam_v, self.step_dev)]
@@ -653,20 +658,33 @@ class SVGPGibbs:
                     all_reduce(self.grad)  # communicator set-up must not happen under capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            if c_fused:
-                self.train_step(self._gx, self._gy, lr, world_size, B_global, all_reduce)
-            else:
-                self.loss_and_grad(self._gx, self._gy, world_size, B_global)
-                if self._g_fused:
-                    if all_reduce is not None:
-                        all_reduce(self.grad)
-                    self.adam_step(lr)
-        # (the graph holds raw pointers into self._i8_bufs, which live as long as the model)
+        self._graphs = []
+        for gx, gy in zip(self._gxs, self._gys):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                if c_fused:
+                    self.train_step(gx, gy, lr, world_size, B_global, all_reduce)
+                else:
+                    self.loss_and_grad(gx, gy, world_size, B_global)
+                    if self._g_fused:
+                        if all_reduce is not None:
+                            all_reduce(self.grad)
+                        self.adam_step(lr)
+            self._graphs.append(graph)
+        self._graph = self._graphs[0]
+        # (the graphs hold raw pointers into the plan workspace / self._i8_bufs, which live as long as the model)
         for t, s in zip((self.theta, self.adam_m, self.adam_v, self.step_dev), snap):
             t.copy_(s)
         self.step_count = int(self.step_dev.item())
+        # pipelined replay (train_step_graph_async): copy stream, per-buffer events, pinned slots for the loss
+        self._g_next = 0
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
+        self._g_done = [torch.cuda.Event() for _ in range(buffers)]
+        self._g_copied = [torch.cuda.Event() for _ in range(buffers)]
+        self._loss_ev = [torch.cuda.Event() for _ in range(buffers)]
+        self._loss_host = torch.zeros(buffers, dtype=torch.float64).pin_memory()
+        for e in self._g_done:
+            e.record()
 
     def train_step_graph(self, xb, yb, all_reduce=None):
         """Replay of the captured step on a new minibatch (xb, yb may live in pinned host memory)."""
@@ -680,6 +698,33 @@ class SVGPGibbs:
         else:
             self.step_count += 1
         return self.grad[-2]
+
+    def train_step_graph_async(self, xb, yb):
+        """Pipelined replay (needs capture(..., buffers >= 2) and a fused graph): the minibatch is copied into the next static
+        input buffer on the copy stream -- ordered only after the step that last READ that buffer, so it runs under the step
+        in flight --, the step is replayed, and its loss is copied to a pinned host slot asynchronously.  Returns a ticket
+        for loss_result(); call that for step k after enqueuing step k + 1 and the host never stalls the device."""
+        assert self._g_fused and len(self._graphs) >= 2, "capture(..., buffers=2) with the collective inside the graph"
+        i = self._g_next
+        cur = torch.cuda.current_stream()
+        self._copy_stream.wait_event(self._g_done[i])
+        with torch.cuda.stream(self._copy_stream):
+            self._gxs[i].copy_(xb, non_blocking=True)
+            self._gys[i].copy_(yb, non_blocking=True)
+            self._g_copied[i].record(self._copy_stream)
+        cur.wait_event(self._g_copied[i])
+        self._graphs[i].replay()
+        self._g_done[i].record(cur)
+        self._loss_host[i:i + 1].copy_(self.grad[-2:-1], non_blocking=True)
+        self._loss_ev[i].record(cur)
+        self.step_count += 1
+        self._g_next = (i + 1) % len(self._graphs)
+        return i
+
+    def loss_result(self, ticket: int) -> float:
+        """The (global) loss of the step train_step_graph_async returned `ticket` for (waits for that step only)."""
+        self._loss_ev[ticket].synchronize()
+        return float(self._loss_host[ticket])
 
     @torch.no_grad()
     def predict(self, xs, chunk: int = 1 << 18):
