@@ -535,7 +535,9 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
   NPGP_CUDA(cudaEventRecord(p->ev[10], sd));   // all the K(X_B,Z) tile kernel needs from this chain; C is only needed by T = K C
   NPGP_CUDA(cudaStreamWaitEvent(sd, p->ev[2], 0));
   NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 1.0, p->E, M, p->P, M, 0.0, p->EP, M, 0, 1, 0, sd));
-  NPGP_TRY(npgp_dgemm(1, 0, M, M, M, 1.0, p->P, M, p->EP, M, 0.0, p->C, M, 2, 0, 0, sd));
+  // C = P^T (E P) is symmetric: only the tiles touching the lower triangle are computed, the rest is mirrored
+  NPGP_TRY(npgp_dgemm(1, 0, M, M, M, 1.0, p->P, M, p->EP, M, 0.0, p->C, M, 2, 0, 1, sd));
+  NPGP_TRY(npgp_symmetrize(M, p->C, M, 0, sd));
   NPGP_TRY(npgp_o8_slice_rows(M, M, p->C, M, 64, p->Cd, p->cexp, sd));
   NPGP_TRY(stamp(p, 2 * SEC_ZZ + 1, sd));
   NPGP_CUDA(cudaEventRecord(p->ev[3], sd));
@@ -625,8 +627,10 @@ static int svgp_backward(npgp_svgp_plan* p, const double* x, const double* theta
   NPGP_TRY(npgp_dgemm(0, 1, M, M, M, 1.0, p->dC, M, p->P, M, 0.0, p->W2, M, 0, 2, 0, sd));
   NPGP_TRY(fork_stream(sd, sd2, p->ev[5]));
   {  // dL_s branch
-    NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 1.0, p->P, M, p->W2, M, 0.0, p->dE, M, 1, 0, 0, sd2));
-    NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 2.0, p->dE, M, p->Ls_t, M, 0.0, p->dLs, M, 0, 1, 0, sd2));
+    // dE = P (dC P^T) is symmetric (lower tiles + mirror); only the lower triangle of dE Ls is used
+    NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 1.0, p->P, M, p->W2, M, 0.0, p->dE, M, 1, 0, 1, sd2));
+    NPGP_TRY(npgp_symmetrize(M, p->dE, M, 0, sd2));
+    NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 2.0, p->dE, M, p->Ls_t, M, 0.0, p->dLs, M, 0, 1, 1, sd2));
     svgp_grad_m_ls_kernel<<<grid2(M), kBlk2, 0, sd2>>>(M, p->dLs, p->Ls_t, p->dm, m, rep / (double)c.N_total,
                                                       grad + p->off_Ls, grad + p->off_m);
     NPGP_LAUNCH_CHECK();
@@ -634,7 +638,9 @@ static int svgp_backward(npgp_svgp_plan* p, const double* x, const double* theta
     if (comm) NPGP_TRY(npgp_allreduce_f64(comm, grad + p->off_m, (long)M + MM, sd2));
     NPGP_CUDA(cudaEventRecord(p->ev[6], sd2));
   }
-  NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 2.0, p->EP, M, p->W2, M, 0.0, p->X, M, 0, 0, 0, sd));
+  // Phi keeps the lower triangle only: the tiles strictly above the diagonal are not computed (half the flops of the
+  // longest product of the chain)
+  NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 2.0, p->EP, M, p->W2, M, 0.0, p->X, M, 0, 0, 1, sd));
   svgp_addr_phi_kernel<<<grid2(M), kBlk2, 0, sd>>>(M, p->X, m, p->dm);
   NPGP_LAUNCH_CHECK();
   NPGP_TRY(npgp_dgemm(1, 0, M, M, M, 1.0, p->P, M, p->X, M, 0.0, p->Y, M, 2, 1, 0, sd));

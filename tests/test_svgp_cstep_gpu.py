@@ -38,7 +38,9 @@ def test_c_step_matches_oracle_and_python_engine(variant, d, B, M):
     for name, gw in want.items():
         assert rel(mc.g[name], gw) < 1e-6, name
     # the two orchestrations launch the same kernels on the same data: they agree far below the oracle tolerance
-    assert abs(loss_c.item() - loss_p.item()) < 1e-10 * abs(loss_p.item())
+    # (C = P^T E P is mirrored from its lower tiles in the C step and computed in full by the Python orchestration: the two
+    # differ by eps * cond(Kzz), like either of them from the oracle)
+    assert abs(loss_c.item() - loss_p.item()) < 1e-8 * abs(loss_p.item())
     for name in mp.g:
         assert rel(mc.g[name], mp.g[name]) < 1e-7, name  # FP64 atomics in both engines; the oracle bound above is the parity claim
     assert rel(mc.last["mu"], mp.last["mu"]) < 1e-8  # (the engines solve K_row W = H with different kernels: cond(K_row) eps)
@@ -50,7 +52,7 @@ def test_c_step_options(variant, opts):
     mc, x, y, Z, p, N = build(variant, "c", B=400, M=128, d=3, seed=2, **opts)
     mp, *_ = build(variant, "python", B=400, M=128, d=3, seed=2, **opts)
     lc, lp = mc.loss_and_grad(x, y, world_size=2), mp.loss_and_grad(x, y, world_size=2)
-    assert abs(lc.item() - lp.item()) < 1e-10 * abs(lp.item())
+    assert abs(lc.item() - lp.item()) < 1e-8 * abs(lp.item())
     for name in mp.g:
         if name == "Z" and opts.get("learn_inducing_locations") is False:
             continue  # frozen by the Adam mask; the engines need not agree on the unused slot
