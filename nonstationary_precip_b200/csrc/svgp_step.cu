@@ -484,7 +484,8 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
   NPGP_LAUNCH_CHECK();
   NPGP_TRY(fork_stream(sd, sd2, p->ev[1]));
   {  // S - I does not depend on the factorisation: runs under the latency-bound Cholesky; so do the KL sums
-    NPGP_TRY(npgp_dgemm(0, 1, M, M, M, 1.0, p->Ls_t, M, p->Ls_t, M, 0.0, p->E, M, 1, 2, 0, sd2));
+    NPGP_TRY(npgp_dgemm(0, 1, M, M, M, 1.0, p->Ls_t, M, p->Ls_t, M, 0.0, p->E, M, 1, 2, 1, sd2));  // symmetric: lower tiles,
+    NPGP_TRY(npgp_symmetrize(M, p->E, M, 0, sd2));                                                  // mirrored
     svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, sd2>>>(M, p->E, M, -1.0);
     NPGP_LAUNCH_CHECK();
     svgp_kl_part_kernel<<<p->nblk_kl, 256, 0, sd2>>>(M, p->Ls_t, m, p->kl_part);
@@ -622,11 +623,12 @@ static int svgp_backward(npgp_svgp_plan* p, const double* x, const double* theta
                                p->syrk_part_bytes, sd));
   NPGP_TRY(stamp(p, 2 * SEC_SYRK + 1, sd));
   NPGP_TRY(stamp(p, 2 * SEC_M3, sd));
-  NPGP_TRY(npgp_gemv_n(M, M, p->P, M, p->du, p->dm, sd));
   // dE = P dC P^T and E dE = (E P)(dC P^T): with W = dC P^T both follow from ONE product
   NPGP_TRY(npgp_dgemm(0, 1, M, M, M, 1.0, p->dC, M, p->P, M, 0.0, p->W2, M, 0, 2, 0, sd));
   NPGP_TRY(fork_stream(sd, sd2, p->ev[5]));
-  {  // dL_s branch
+  {  // dL_s branch (and dm = P du, which the main chain needs only after its next product)
+    NPGP_TRY(npgp_gemv_n(M, M, p->P, M, p->du, p->dm, sd2));
+    NPGP_CUDA(cudaEventRecord(p->ev[11], sd2));
     // dE = P (dC P^T) is symmetric (lower tiles + mirror); only the lower triangle of dE Ls is used
     NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 1.0, p->P, M, p->W2, M, 0.0, p->dE, M, 1, 0, 1, sd2));
     NPGP_TRY(npgp_symmetrize(M, p->dE, M, 0, sd2));
@@ -641,6 +643,7 @@ static int svgp_backward(npgp_svgp_plan* p, const double* x, const double* theta
   // Phi keeps the lower triangle only: the tiles strictly above the diagonal are not computed (half the flops of the
   // longest product of the chain)
   NPGP_TRY(npgp_dgemm(0, 0, M, M, M, 2.0, p->EP, M, p->W2, M, 0.0, p->X, M, 0, 0, 1, sd));
+  NPGP_CUDA(cudaStreamWaitEvent(sd, p->ev[11], 0));  // dm
   svgp_addr_phi_kernel<<<grid2(M), kBlk2, 0, sd>>>(M, p->X, m, p->dm);
   NPGP_LAUNCH_CHECK();
   NPGP_TRY(npgp_dgemm(1, 0, M, M, M, 1.0, p->P, M, p->X, M, 0.0, p->Y, M, 2, 1, 0, sd));
