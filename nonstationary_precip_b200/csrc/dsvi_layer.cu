@@ -168,7 +168,7 @@ extern "C" int npgp_dsvi_layer_fwd(int n, int M, int d, const double* X, const d
   svgp_add_diag_kernel<<<ceil_div(M, 256), 256, 0, st>>>(M, w.Kzz, M, jitter);
   NPGP_LAUNCH_CHECK();
   NPGP_TRY(npgp_potrf_inv_flow(M, w.Kzz, M, w.P, M, w.flags, w.flags_bytes, info, st));
-  svgp_tri_skinny_t_kernel<1><<<ceil_div(M, 32), 256, 0, st>>>(M, w.P, m, w.u);
+  svgp_tri_skinny_t_kernel<1><<<ceil_div(M, 8), 256, 0, st>>>(M, w.P, m, w.u);
   NPGP_LAUNCH_CHECK();
   svgp_tril_copy_kernel<<<g2(M), kB2, 0, st>>>(M, Ls, w.Ls_t);
   NPGP_LAUNCH_CHECK();

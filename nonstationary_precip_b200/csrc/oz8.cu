@@ -731,7 +731,9 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
     ++rb;
   }
   const int cb = 2 * rb + tl;
-  constexpr int EPT = O8_BM * O8_BN / 256;  // elements per thread: e = threadIdx.x + 256 i (coalesced)
+  constexpr int NSPLIT = 4;                           // CTAs per tile (blockIdx.y): 32 rows each
+  constexpr int EPT = O8_BM * O8_BN / 256 / NSPLIT;   // elements per thread: e = e0 + threadIdx.x + 256 i (coalesced)
+  const int e0 = blockIdx.y * (O8_BM * O8_BN / NSPLIT);
   double acc[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; ++i) acc[i] = 0.0;
@@ -743,7 +745,7 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int item = chunk * n_tiles + tile;
       if (item < probe.full * n_cta) {  // a full-wave item: one segment, owned by CTA item % n_cta as its (item / n_cta)-th
-        const double* src = part + ((long)(item % n_cta) * slots_per_cta + item / n_cta) * (O8_BM * O8_BN) + threadIdx.x;
+        const double* src = part + ((long)(item % n_cta) * slots_per_cta + item / n_cta) * (O8_BM * O8_BN) + e0 + threadIdx.x;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) acc[i] += src[256 * i];
         continue;
@@ -756,7 +758,7 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
         int t2, k0, k1, idx = probe.full;
         while (it.next(t2, k0, k1)) {
           if (t2 == tile && k0 / aspc == chunk) {
-            const double* src = part + ((long)c * slots_per_cta + idx) * (O8_BM * O8_BN) + threadIdx.x;
+            const double* src = part + ((long)c * slots_per_cta + idx) * (O8_BM * O8_BN) + e0 + threadIdx.x;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) acc[i] += src[256 * i];
           }
@@ -769,7 +771,7 @@ __global__ void __launch_bounds__(256) o8_syrk_finish_kernel(int M, int nks_tota
   const double scale = alpha * (w0 ? w0[0] : 1.0);
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const int e = threadIdx.x + 256 * i;
+    const int e = e0 + threadIdx.x + 256 * i;
     const int r = rb * O8_BM + e / O8_BN, c = cb * O8_BN + e % O8_BN;
     if (c < r) continue;
     double s = acc[i];
@@ -1051,7 +1053,7 @@ static int o8_syrk_launch(int M, int nks, const int8_t* Xs, const int* ex, const
     o8_syrk_kernel<MN, false><<<grid, O8_THREADS, O8_SY_SMEM, stream>>>(M, nks, spc, slots, Xs, ex, x_scale, uniform_count,
                                                                        uniform_target, part, tmA, tmB);
   NPGP_LAUNCH_CHECK();
-  o8_syrk_finish_kernel<<<n_tiles, 256, 0, stream>>>(M, nks, spc, grid, slots, part, alpha, w0_dev, uniform_count, uniform_target,
+  o8_syrk_finish_kernel<<<dim3(n_tiles, 4), 256, 0, stream>>>(M, nks, spc, grid, slots, part, alpha, w0_dev, uniform_count, uniform_target,
                                                      accumulate, Out, ldo, skip_count, skip_rows, MN ? Xs : nullptr, x_scale);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;

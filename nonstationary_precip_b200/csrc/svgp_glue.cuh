@@ -69,36 +69,36 @@ static __global__ void __launch_bounds__(256) svgp_tri_skinny_n_kernel(int M, co
   }
 }
 
-// W = P^T T: CTA = 32 columns j x 8 row groups; thread (g, j) adds rows i = j + g, j + g + 8, ... (P is read coalesced along j),
-// the eight groups are combined in index order through shared memory (bitwise reproducible; no atomics)
+// W = P^T T: one warp per output row j (= column j of P), lanes over the rows i = j + lane, j + lane + 32, ...; the column
+// access is a 32-line gather per load, but P was written a moment ago and sits in L2, and 1024 warps keep ~M^2/2 gathered
+// sectors in flight (a first version with a coalesced walk down the rows, 32 CTAs x 128 dependent iterations, took 60 us).
+// Fixed lane / shuffle order: bitwise reproducible, no atomics.
 template <int KP>
 static __global__ void __launch_bounds__(256) svgp_tri_skinny_t_kernel(int M, const double* __restrict__ P, const double* __restrict__ T,
-                                                                double* __restrict__ W) {
-  __shared__ double sm[8][32][KP + 1];
-  const int jl = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + jl;
-  double a[KP];
+                                                                       double* __restrict__ W) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (j >= M) return;
+  double a[KP], b[KP];
 #pragma unroll
-  for (int c = 0; c < KP; ++c) a[c] = 0.0;
-  if (j < M) {
-    for (int i = blockIdx.x * 32 + g; i < M; i += 8) {
-      if (i < j) continue;
-      const double pv = P[(long)i * M + j];
-#pragma unroll
-      for (int c = 0; c < KP; ++c) a[c] = fma(pv, T[(long)i * KP + c], a[c]);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < KP; ++c) sm[g][jl][c] = a[c];
-  __syncthreads();
-  if (g == 0 && j < M) {
+  for (int c = 0; c < KP; ++c) a[c] = b[c] = 0.0;
+  int i = j + lane;
+  for (; i + 32 < M; i += 64) {  // two independent chains
+    const double p0 = P[(long)i * M + j], p1 = P[(long)(i + 32) * M + j];
 #pragma unroll
     for (int c = 0; c < KP; ++c) {
-      double t = sm[0][jl][c];
-#pragma unroll
-      for (int k = 1; k < 8; ++k) t += sm[k][jl][c];
-      W[(long)j * KP + c] = t;
+      a[c] = fma(p0, T[(long)i * KP + c], a[c]);
+      b[c] = fma(p1, T[(long)(i + 32) * KP + c], b[c]);
     }
+  }
+  if (i < M) {
+    const double p0 = P[(long)i * M + j];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) a[c] = fma(p0, T[(long)i * KP + c], a[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < KP; ++c) {
+    const double t = warp_sum(a[c] + b[c]);
+    if (lane == 0) W[(long)j * KP + c] = t;
   }
 }
 

@@ -344,14 +344,14 @@ template <int KP>
 int tri_skinny(int M, const double* Pm, const double* R, double* tmp, double* out, cudaStream_t st) {
   svgp_tri_skinny_n_kernel<KP><<<ceil_div(M, 8), 256, 0, st>>>(M, Pm, R, tmp);
   NPGP_LAUNCH_CHECK();
-  svgp_tri_skinny_t_kernel<KP><<<ceil_div(M, 32), 256, 0, st>>>(M, Pm, tmp, out);
+  svgp_tri_skinny_t_kernel<KP><<<ceil_div(M, 8), 256, 0, st>>>(M, Pm, tmp, out);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
 
 // out = P^T w (M): the transposed skinny product alone (u = P^T m)
 int tri_t_vec(int M, const double* Pm, const double* w, double* out, cudaStream_t st) {
-  svgp_tri_skinny_t_kernel<1><<<ceil_div(M, 32), 256, 0, st>>>(M, Pm, w, out);
+  svgp_tri_skinny_t_kernel<1><<<ceil_div(M, 8), 256, 0, st>>>(M, Pm, w, out);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
 }
@@ -579,8 +579,7 @@ static int svgp_forward(npgp_svgp_plan* p, const double* x, const double* y, con
   NPGP_TRY(stamp(p, 2 * SEC_RQ, st));
   NPGP_TRY(npgp_o8_rowquad_digits(B, M, p->Ad, nullptr, s, p->Cd, p->cexp, nullptr, 0, p->T, M, p->q_part, B, p->gmu0,
                                   p->du_part, st));
-  NPGP_TRY(npgp_o8_sum_partials(p->nb128, M, p->du_part, p->du, st));
-  NPGP_TRY(stamp(p, 2 * SEC_RQ + 1, st));
+  NPGP_TRY(stamp(p, 2 * SEC_RQ + 1, st));  // (the partial column sums du_part are added up in the backward, off this stream)
   NPGP_TRY(stamp(p, 2 * SEC_ELL, st));
   NPGP_CUDA(cudaMemsetAsync(p->skip_count, 0, sizeof(int), st));
   NPGP_TRY(npgp_gauss_ell_parts(B, y, p->mu, p->q_part, M / 64, B, s, c.jitter_xx, c.min_var, noise, 1.0 / c.B_global, nullptr,
@@ -627,6 +626,7 @@ static int svgp_backward(npgp_svgp_plan* p, const double* x, const double* theta
   NPGP_TRY(npgp_dgemm(0, 1, M, M, M, 1.0, p->dC, M, p->P, M, 0.0, p->W2, M, 0, 2, 0, sd));
   NPGP_TRY(fork_stream(sd, sd2, p->ev[5]));
   {  // dL_s branch (and dm = P du, which the main chain needs only after its next product)
+    NPGP_TRY(npgp_o8_sum_partials(p->nb128, M, p->du_part, p->du, sd2));  // du = K^T g_mu from the row-block partials
     NPGP_TRY(npgp_gemv_n(M, M, p->P, M, p->du, p->dm, sd2));
     NPGP_CUDA(cudaEventRecord(p->ev[11], sd2));
     // dE = P (dC P^T) is symmetric (lower tiles + mirror); only the lower triangle of dE Ls is used
