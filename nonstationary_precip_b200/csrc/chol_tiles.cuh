@@ -127,7 +127,9 @@ __device__ __forceinline__ void acc_axpy_global(const double (&acc)[2][4][2], do
 // ---------------------------------------------------------------------------------------------------------------------
 // 8x8 pivot block, one thread, registers.  (Measured alternatives, both slower on B200: a float-seeded rsqrt with two
 // Newton steps, 2330 vs 1660 cycles, and a square-root-free elimination that keeps only a reciprocal on the pivot chain,
-// 1880 cycles -- the block is bound by the ~400 instructions one thread has to issue, not by the rsqrt latency.)
+// 1880 cycles -- the block is bound by the ~400 instructions one thread has to issue, not by the rsqrt latency.  Round 2:
+// the same block on 8 lanes of a warp (row per lane, shuffles for the pivot column, ~150 warp instructions) is slower too:
+// the dependent shuffles cost more than the issue slots they save, potrf at M = 1024 went 0.460 -> 0.482 ms.)
 __device__ __forceinline__ void chol8_serial(double* s, double* sInv, int c0, int global_offset,
                                              int* __restrict__ info) {
   double a[8][8], inv[8];
