@@ -51,20 +51,29 @@ static __global__ void svgp_sym_avg_kernel(int M, const double* __restrict__ A, 
 // ~30 us of pure latency on them.  Y = P R: one warp per output row (fixed lane / shuffle order).
 template <int KP>
 static __global__ void __launch_bounds__(256) svgp_tri_skinny_n_kernel(int M, const double* __restrict__ P, const double* __restrict__ R,
-                                                                double* __restrict__ Y) {
+                                                                       double* __restrict__ Y) {
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= M) return;
-  double a[KP];
+  double a[KP], b[KP];
 #pragma unroll
-  for (int c = 0; c < KP; ++c) a[c] = 0.0;
-  for (int j = lane; j <= i; j += 32) {
-    const double pv = P[(long)i * M + j];
+  for (int c = 0; c < KP; ++c) a[c] = b[c] = 0.0;
+  int j = lane;
+  for (; j + 32 <= i; j += 64) {  // two independent chains
+    const double p0 = P[(long)i * M + j], p1 = P[(long)i * M + j + 32];
 #pragma unroll
-    for (int c = 0; c < KP; ++c) a[c] = fma(pv, R[(long)j * KP + c], a[c]);
+    for (int c = 0; c < KP; ++c) {
+      a[c] = fma(p0, R[(long)j * KP + c], a[c]);
+      b[c] = fma(p1, R[(long)(j + 32) * KP + c], b[c]);
+    }
+  }
+  if (j <= i) {
+    const double p0 = P[(long)i * M + j];
+#pragma unroll
+    for (int c = 0; c < KP; ++c) a[c] = fma(p0, R[(long)j * KP + c], a[c]);
   }
 #pragma unroll
   for (int c = 0; c < KP; ++c) {
-    const double t = warp_sum(a[c]);
+    const double t = warp_sum(a[c] + b[c]);
     if (lane == 0) Y[(long)i * KP + c] = t;
   }
 }
