@@ -21,8 +21,8 @@
 // The SYRK contracts over the ROWS of K.  With a matrix-wide scale it reads the same row-layout planes MN-major
 // (instruction descriptor a_major = b_major = 1; verified by tools/probes/umma_i8_probe2.cu), each operand tile fetched by
 // one 5-D TMA box; with per-column scales (general operands) it reads transposed planes written by o8_slice_t_kernel.
-// Chunks of <= 8192 rows keep int32 exact; every (tile, chunk) item stores its FP64 partial and a finishing kernel adds the
-// chunks in a fixed order (no FP64 atomics: results are bitwise reproducible).
+// Row chunks of <= 16384 rows keep int32 exact; every (tile, chunk) segment stores its FP64 partial tile and a finishing kernel
+// adds a tile's segments in a fixed order (no FP64 atomics: results are bitwise reproducible).  Work decomposition: O8SegIter.
 // Descriptor encodings: cute/arch/mma_sm100_desc.hpp of the vendored CUTLASS.
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cstring>
