@@ -457,7 +457,17 @@ def run_ours(args):
                                         "(nominal 148 SM x 64 FMA x 2 x 1.965 GHz = 37.2)"},
             "roofline_kxz": {"bound": "hbm", "kernel": "gibbs_%s fwd+bwd (K written, T read: 16 B/pair)" % args.variant,
                              "achieved": kxz_gbs, "peak": hbm, "unit": "GB/s", "frac": kxz_gbs / hbm,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                             # the roof these tile kernels actually sit under: FP64 instructions per pair counted in the SASS of
+                             # the inner loops (cuobjdump) x pairs / measured time, against the DFMA issue
+                             # peak of 148 SMs x 64 lanes x 1.965 GHz; ncu: sm__pipe_fp64_cycles_active 75 % (fwd) / 65 % (bwd)
+                             "fp64_pipe": None if args.variant != "full" else {
+                                 "dp_instr_per_pair": {"fwd": 73, "bwd": 160},
+                                 "achieved_dp_instr_per_s": (73 + 160) * float(Bl) * M_IND / ((sec["kxz_fwd"] + sec["kxz_bwd"]) * 1e-3),
+                                 "peak_dp_instr_per_s": 148 * 64 * 1.965e9,
+                                 "frac": (73 + 160) * float(Bl) * M_IND / ((sec["kxz_fwd"] + sec["kxz_bwd"]) * 1e-3) / (148 * 64 * 1.965e9),
+                                 "ncu_pipe_fp64_active": {"fwd": 0.751, "bwd": 0.647,
+                                                          "source": "profiles/r02_ncu_full_step_kernels_final.txt"}}},
             # one eager single-stream step, CUDA events per section (sections overlap in the timed graph replay):
             # replicated = work every rank repeats (O(M^3) chain on Kzz, assembly, all-reduce, Adam); sharded = work on this
             # rank's B/G rows.  The Amdahl table in DESIGN.md is built from these.
