@@ -204,8 +204,6 @@ extern "C" int npgp_dsvi_layer_bwd(int n, int M, int d, const double* X, const d
   DsviWs w;
   NPGP_TRY(dsvi_layout(n, M, d, work, &w));
   if (work_bytes < w.total) return NPGP_EWORKSPACE;
-  const long MM = (long)M * M;
-  (void)MM;
   // ---- seeds
   NPGP_CUDA(cudaMemsetAsync(w.cnt_sum, 0, 2 * sizeof(double), st));
   dsvi_seed_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, dvar, var, min_var, w.gv, w.gv2, w.cnt_sum);

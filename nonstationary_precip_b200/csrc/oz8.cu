@@ -566,7 +566,6 @@ o8_syrk_kernel(int M, int nks_total, int spc, int slots_per_cta, const int8_t* _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rb = M / O8_BM, n_cb = M / O8_BN;
   const int n_tiles = n_rb * n_cb - n_rb * (n_rb - 1);  // sum_rb (n_cb - 2 rb): tiles with cb >= 2 rb
-  const int nks_cols = M / O8_KS;  // k-steps per row block of the row layout (MN only)
   auto tile_rc = [&](int tl, int& rb, int& cb) {
     rb = 0;
     while (tl >= n_cb - 2 * rb) {

@@ -19,7 +19,6 @@
 //                                diag : [Z (M,d) | log_ell_z (d,M)   | m (M) | Ls (M,M) | raw_outputscale | raw_noise]
 // padded to an even count n_pad; grad has n_pad + 2 entries, grad[n_pad] = this rank's share of -ELBO (so ONE all-reduce
 // of grad carries gradient and loss).
-#include <cstdio>
 #include <cstring>
 #include <new>
 
