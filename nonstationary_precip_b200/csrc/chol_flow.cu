@@ -86,7 +86,28 @@ __device__ __forceinline__ void zero_tile_global(double* __restrict__ G, long ld
   }
 }
 
-// flags: [0, nb^2) L tiles (i * nb + k), [nb^2, 2 nb^2) P tiles, [2 nb^2] abort
+// full 64 x 64 tile (leading dimension 64 in global memory) <-> shared tile: the hand-over of S_{k+1,k} (below)
+__device__ __forceinline__ void store_full(const double* s, double* __restrict__ G) {
+  for (int e = threadIdx.x; e < TB * TB; e += CT) G[e] = s[(e >> 6) * TLD + (e & 63)];
+}
+__device__ __forceinline__ void load_full_cg(double* s, const double* __restrict__ G) {
+  for (int e = threadIdx.x; e < TB * TB / 2; e += CT) {
+    const double2 t = __ldcg(reinterpret_cast<const double2*>(G) + e);
+    const int r = e >> 5, c = (e & 31) * 2;
+    s[r * TLD + c] = t.x;
+    s[r * TLD + c + 1] = t.y;
+  }
+}
+
+static inline long flow_flag_ints(long nb) { return 2 * nb * nb + 16 + nb; }
+static inline long flow_scratch_offset(long nb) { return (flow_flag_ints(nb) * (long)sizeof(int) + 255) & ~255L; }
+
+// flags: [0, nb^2) L tiles (i * nb + k), [nb^2, 2 nb^2) P tiles, [2 nb^2] abort, [2 nb^2 + 1, + nb) S tiles;
+// scratch (after the flags, 256-byte aligned): nb tiles of 64 x 64 doubles.
+// Hand-over of the sub-diagonal tile: the task of tile (k+1,k) publishes S = A_{k+1,k} - sum_{j<k} L_{k+1,j} L_{k,j}^T as soon as
+// it has it (long before P_kk exists); the task of the NEXT diagonal tile (k+1,k+1) then forms L_{k+1,k} = S P_kk^T itself the
+// moment P_kk is published, instead of waiting for the (k+1,k) task to compute, store and flag the same product: one flag hop,
+// one global store and one L2 load less on the critical path of every column (same operands, same MMA order: same bits).
 // Up to kFlowBatch independent matrices of the same order are factored by ONE launch: CTA x works on matrix x % n, task
 // x / n.  Interleaving keeps every matrix's own task order (dependencies still point to lower block indices), and the early
 // (critical-path) tasks of ALL matrices are resident from the start -- two concurrent single-matrix launches instead
@@ -97,6 +118,7 @@ struct FlowBatch {
   double* P[kFlowBatch];
   int* flags[kFlowBatch];
   int* info[kFlowBatch];
+  double* S[kFlowBatch];
   int n;
 };
 
@@ -106,11 +128,13 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, const 
   double* __restrict__ P = fb.P[which];
   int* __restrict__ flags = fb.flags[which];
   int* __restrict__ info = fb.info[which];
+  double* __restrict__ Sg = fb.S[which];
   extern __shared__ double sm[];
   double *bufA = sm, *bufB = sm + TILE_SMEM, *bufC = sm + 2 * TILE_SMEM;
   int* Lf = flags;
   int* Pf = flags + nb * nb;
   int* abort_flag = flags + 2 * nb * nb;
+  int* Sf = flags + 2 * nb * nb + 1;
   const WarpPos p;
   const int nL = nb * (nb + 1) / 2;
   int t = blockIdx.x / fb.n;
@@ -132,6 +156,23 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, const 
     double upd[2][4][2];
     acc_zero(upd);
     for (int j = 0; j < k; ++j) {
+      if (i == k && j == k - 1) {
+        // last update of a diagonal tile: L_{k,k-1} = S P_{k-1,k-1}^T is formed here (see the note above the kernel)
+        flow_wait(&Sf[k - 1], abort_flag, info);
+        load_full_cg(bufA, Sg + (long)(k - 1) * TB * TB);
+        flow_wait(&Lf[(k - 1) * nb + (k - 1)], abort_flag, info);
+        load_tile_cg(bufB, P, ldp, (k - 1) * TB, (k - 1) * TB, M);
+        __syncthreads();
+        double lk[2][4][2];
+        acc_zero(lk);
+        mma_64<false, true>(lk, bufA, bufB, p);
+        __syncthreads();
+        acc_to_smem(lk, bufA, p, 1.0);
+        __syncthreads();
+        mma_64<false, true>(upd, bufA, bufA, p);
+        __syncthreads();
+        continue;
+      }
       flow_wait(&Lf[i * nb + j], abort_flag, info);
       if (i != k) flow_wait(&Lf[k * nb + j], abort_flag, info);
       load_tile_cg(bufA, A, lda, i * TB, j * TB, M);
@@ -151,6 +192,10 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, const 
         bufC[r * TLD + c + 1] -= upd[mt][nt][1];
       }
     __syncthreads();
+    if (i == k + 1) {  // publish S for the next diagonal task
+      store_full(bufC, Sg + (long)k * TB * TB);
+      flow_signal(&Sf[k]);
+    }
     if (i == k) {
       factor_invert_64(bufC, bufB, bufA, k * TB, info);
       store_tile(bufB, P, ldp, k * TB, k * TB, M);
@@ -201,10 +246,10 @@ __global__ void __launch_bounds__(CT, 2) potrf_flow_kernel(int M, int nb, const 
 
 using namespace npgp;
 
-// flags (ints): 2 * nb^2 + 1, nb = ceil(M / 64)
+// flags (ints) + nb scratch tiles, nb = ceil(M / 64)
 extern "C" long npgp_potrf_flow_workspace_bytes(int M) {
   const long nb = ((long)M + TB - 1) / TB;
-  return (2 * nb * nb + 16) * (long)sizeof(int);
+  return flow_scratch_offset(nb) + nb * TB * TB * (long)sizeof(double);
 }
 
 // A (M x M, symmetric, lower part used) -> L in place (strict upper triangle zeroed), P = L^-1; *info = 0, the 1-based index
@@ -219,11 +264,13 @@ extern "C" int npgp_potrf_inv_flow(int M, double* A, long lda, double* P, long l
   if (work_bytes < npgp_potrf_flow_workspace_bytes(M)) return NPGP_EWORKSPACE;
   const int nb = (M + TB - 1) / TB;
   NPGP_CUDA(cudaFuncSetAttribute(potrf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_SMEM));
-  NPGP_CUDA(cudaMemsetAsync(work, 0, (size_t)npgp_potrf_flow_workspace_bytes(M), stream));
+  if (reinterpret_cast<uintptr_t>(work) & 15) return NPGP_EUNSUPPORTED;
+  NPGP_CUDA(cudaMemsetAsync(work, 0, (size_t)flow_flag_ints(nb) * sizeof(int), stream));  // the flags; the scratch tiles need none
   NPGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int), stream));
   FlowBatch fb;
   fb.n = 1;
   fb.A[0] = A, fb.P[0] = P, fb.flags[0] = static_cast<int*>(work), fb.info[0] = info;
+  fb.S[0] = reinterpret_cast<double*>(static_cast<char*>(work) + flow_scratch_offset(nb));
   potrf_flow_kernel<<<nb * nb, CT, FLOW_SMEM, stream>>>(M, nb, fb, lda, ldp);
   NPGP_LAUNCH_CHECK();
   return NPGP_OK;
@@ -241,13 +288,16 @@ extern "C" int npgp_potrf_inv_flow_batch(int n, int M, double* const* A, long ld
   fb.n = n;
   for (int i = 0; i < n; ++i) {
     if (!A[i] || !P[i] || !work[i] || !info[i]) return NPGP_EINVAL;
-    if ((reinterpret_cast<uintptr_t>(A[i]) & 15) || (reinterpret_cast<uintptr_t>(P[i]) & 15)) return NPGP_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(A[i]) & 15) || (reinterpret_cast<uintptr_t>(P[i]) & 15) ||
+        (reinterpret_cast<uintptr_t>(work[i]) & 15))
+      return NPGP_EUNSUPPORTED;
     fb.A[i] = A[i], fb.P[i] = P[i], fb.flags[i] = static_cast<int*>(work[i]), fb.info[i] = info[i];
   }
   const int nb = (M + TB - 1) / TB;
+  for (int i = 0; i < n; ++i) fb.S[i] = reinterpret_cast<double*>(static_cast<char*>(work[i]) + flow_scratch_offset(nb));
   NPGP_CUDA(cudaFuncSetAttribute(potrf_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FLOW_SMEM));
   for (int i = 0; i < n; ++i) {
-    NPGP_CUDA(cudaMemsetAsync(work[i], 0, (size_t)npgp_potrf_flow_workspace_bytes(M), stream));
+    NPGP_CUDA(cudaMemsetAsync(work[i], 0, (size_t)flow_flag_ints(nb) * sizeof(int), stream));
     NPGP_CUDA(cudaMemsetAsync(info[i], 0, sizeof(int), stream));
   }
   potrf_flow_kernel<<<n * nb * nb, CT, FLOW_SMEM, stream>>>(M, nb, fb, lda, ldp);
